@@ -1,0 +1,638 @@
+/*
+ * oracle.c — CPU restatement of the halo2-regex witness-generation path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this file's
+ * shared object.  The product (halo2_regex_b200/) never links, imports or calls it.
+ *
+ * The reference (zkemail/halo2-regex, Rust, halo2-base 0.2.2 @ axiom-crypto/halo2-lib rev 9860acc) cannot be compiled
+ * in this image (no rustc/cargo, no network).  This file therefore restates, step by step and with the same
+ * data-structure shapes (a hash map keyed (u8,u64), hash sets of (u64,u64), linear `contains` scans, per-call
+ * vectors), the following reference code (paths relative to the reference root):
+ *     src/defs.rs:75-110, 209-265      the two text parsers
+ *     src/table.rs:101-122, 129-193    table row order (defines the multiplicity bins)
+ *     src/lib.rs:804-823               derive_states
+ *     src/lib.rs:825-845               derive_substr_ids
+ *     src/lib.rs:847-888               derive_is_start_end
+ *     src/lib.rs:339-348, 388-418      enable / char / state / substr_id padding rules
+ *     src/lib.rs:427-457               accept rule
+ *     src/lib.rs:459-519               cross-def sums, start_enable / end_enable
+ *     src/lib.rs:598-645, 663-714      start_mask / end_mask scans (halo2-base FlexGate semantics on {0,1}:
+ *                                      select(a,b,sel) = sel*(a-b)+b, and = a*b, not = 1-a, is_equal = [a==b])
+ *     src/lib.rs:740-764               masked outputs
+ *     src/lib.rs:218-232, 247-257, 273-283   lookup input tuples (multiplicities are DEFINED as their histogram)
+ *
+ * Parity pinning: masked_characters / all_substr_ids are pinned by the reference's own literal expectations
+ * (G1, G2, G4, G5: src/lib.rs:1069-1110, 1318-1364; G9: examples/regex.rs:185-206) and the accept flag by the
+ * reference's negative tests (G3, G6-G8) — see tests/test_oracle_golden.py.  The state column, per-def substr ids and
+ * start/end enables are pinned only through the reference's constraint system (first-state gate, transition lookup,
+ * endpoint lookups), which tests/test_oracle_golden.py re-checks row by row against the table rows.
+ * Multiplicities, compact substring records and the status record have no reference counterpart: PARITY UNPINNED
+ * (defined in include/b2r.h; self-checked by sum(mult) = N*M).
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/b2r.h"
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* HashMap<(u8,u64),(usize,u64)> — open addressing (the reference uses std::collections::HashMap/SipHash-1-3;
+ * a cheaper hash only makes this CPU baseline faster than the real reference). */
+typedef struct {
+    uint8_t used, ch;
+    uint64_t state, line_idx, next;
+} map_slot;
+typedef struct {
+    map_slot* slots;
+    uint64_t cap, len;
+} lookup_map;
+
+static uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+static void map_init(lookup_map* m, uint64_t cap) {
+    m->cap = cap; m->len = 0; m->slots = (map_slot*)calloc(cap, sizeof(map_slot));
+}
+static void map_insert(lookup_map* m, uint8_t ch, uint64_t state, uint64_t line_idx, uint64_t next);
+static void map_grow(lookup_map* m) {
+    lookup_map n; map_init(&n, m->cap * 2);
+    for (uint64_t i = 0; i < m->cap; i++)
+        if (m->slots[i].used) map_insert(&n, m->slots[i].ch, m->slots[i].state, m->slots[i].line_idx, m->slots[i].next);
+    free(m->slots); *m = n;
+}
+static void map_insert(lookup_map* m, uint8_t ch, uint64_t state, uint64_t line_idx, uint64_t next) {
+    if ((m->len + 1) * 2 > m->cap) map_grow(m);
+    uint64_t h = mix64(state * 256 + ch) & (m->cap - 1);
+    while (m->slots[h].used) {
+        if (m->slots[h].ch == ch && m->slots[h].state == state) { /* HashMap::insert overwrites the value */
+            m->slots[h].line_idx = line_idx; m->slots[h].next = next; return;
+        }
+        h = (h + 1) & (m->cap - 1);
+    }
+    m->slots[h].used = 1; m->slots[h].ch = ch; m->slots[h].state = state;
+    m->slots[h].line_idx = line_idx; m->slots[h].next = next; m->len++;
+}
+static const map_slot* map_get(const lookup_map* m, uint8_t ch, uint64_t state) {
+    uint64_t h = mix64(state * 256 + ch) & (m->cap - 1);
+    while (m->slots[h].used) {
+        if (m->slots[h].ch == ch && m->slots[h].state == state) return &m->slots[h];
+        h = (h + 1) & (m->cap - 1);
+    }
+    return NULL;
+}
+
+/* HashSet<(u64,u64)> */
+typedef struct { uint8_t used; uint64_t a, b; } set_slot;
+typedef struct { set_slot* slots; uint64_t cap, len; } pair_set;
+static void set_init(pair_set* s, uint64_t cap) { s->cap = cap; s->len = 0; s->slots = (set_slot*)calloc(cap, sizeof(set_slot)); }
+static void set_insert(pair_set* s, uint64_t a, uint64_t b);
+static void set_grow(pair_set* s) {
+    pair_set n; set_init(&n, s->cap * 2);
+    for (uint64_t i = 0; i < s->cap; i++) if (s->slots[i].used) set_insert(&n, s->slots[i].a, s->slots[i].b);
+    free(s->slots); *s = n;
+}
+static void set_insert(pair_set* s, uint64_t a, uint64_t b) {
+    if ((s->len + 1) * 2 > s->cap) set_grow(s);
+    uint64_t h = mix64(a * 0x9E3779B97F4A7C15ULL + b) & (s->cap - 1);
+    while (s->slots[h].used) {
+        if (s->slots[h].a == a && s->slots[h].b == b) return;
+        h = (h + 1) & (s->cap - 1);
+    }
+    s->slots[h].used = 1; s->slots[h].a = a; s->slots[h].b = b; s->len++;
+}
+static int set_contains(const pair_set* s, uint64_t a, uint64_t b) {
+    uint64_t h = mix64(a * 0x9E3779B97F4A7C15ULL + b) & (s->cap - 1);
+    while (s->slots[h].used) {
+        if (s->slots[h].a == a && s->slots[h].b == b) return 1;
+        h = (h + 1) & (s->cap - 1);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* text → lines → u64 tokens, as BufRead::lines + str::split_whitespace + str::parse::<u64> do */
+typedef struct { uint64_t* v; uint64_t n, cap; } u64vec;
+static void vec_push(u64vec* v, uint64_t x) {
+    if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 8; v->v = (uint64_t*)realloc(v->v, v->cap * sizeof(uint64_t)); }
+    v->v[v->n++] = x;
+}
+
+/* length (1..3) of a Unicode White_Space code point encoded at p, or 0 */
+static int ws_len(const unsigned char* p, const unsigned char* end) {
+    unsigned c = p[0];
+    if ((c >= 0x09 && c <= 0x0d) || c == 0x20) return 1;
+    if (c == 0xC2 && p + 1 < end && (p[1] == 0x85 || p[1] == 0xA0)) return 2;
+    if (p + 2 < end) {
+        if (c == 0xE1 && p[1] == 0x9A && p[2] == 0x80) return 3;                       /* U+1680 */
+        if (c == 0xE2 && p[1] == 0x80 && ((p[2] >= 0x80 && p[2] <= 0x8A) || p[2] == 0xA8 || p[2] == 0xA9 || p[2] == 0xAF)) return 3;
+        if (c == 0xE2 && p[1] == 0x81 && p[2] == 0x9F) return 3;                       /* U+205F */
+        if (c == 0xE3 && p[1] == 0x80 && p[2] == 0x80) return 3;                       /* U+3000 */
+    }
+    return 0;
+}
+/* parse one line into tokens; returns 0 ok, -1 on a token that is not a u64 (Rust: optional '+', digits, no overflow) */
+static int parse_line(const unsigned char* p, const unsigned char* end, u64vec* out) {
+    out->n = 0;
+    while (p < end) {
+        int w = ws_len(p, end);
+        if (w) { p += w; continue; }
+        const unsigned char* q = p;
+        while (q < end && !ws_len(q, end)) q++;
+        const unsigned char* t = p;
+        if (*t == '+') t++;
+        if (t == q) return -1;
+        uint64_t val = 0;
+        for (; t < q; t++) {
+            if (*t < '0' || *t > '9') return -1;
+            unsigned d = *t - '0';
+            if (val > (UINT64_MAX - d) / 10) return -1;
+            val = val * 10 + d;
+        }
+        vec_push(out, val);
+        p = q;
+    }
+    return 0;
+}
+/* iterate lines like BufRead::lines: split at '\n', strip one trailing '\r', no empty line after a final '\n' */
+static int next_line(const char* text, size_t len, size_t* pos, const unsigned char** b, const unsigned char** e) {
+    if (*pos >= len) return 0;
+    size_t s = *pos, i = s;
+    while (i < len && text[i] != '\n') i++;
+    size_t stop = i;
+    if (i < len && stop > s && text[stop - 1] == '\r') stop--;
+    *b = (const unsigned char*)text + s; *e = (const unsigned char*)text + stop;
+    *pos = (i < len) ? i + 1 : i;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+typedef struct orc_allstr {
+    lookup_map state_lookup;
+    uint64_t first_state_val, accepted_state_val, largest_state_val;
+} orc_allstr;
+
+typedef struct orc_substr {
+    uint64_t max_length, min_position, max_position;
+    pair_set valid_state_transitions;
+    u64vec start_states, end_states;
+} orc_substr;
+
+/* reference src/defs.rs:75-110 */
+int orc_allstr_parse(const char* text, size_t len, orc_allstr** out, uint64_t* err_line) {
+    orc_allstr* a = (orc_allstr*)calloc(1, sizeof(orc_allstr));
+    map_init(&a->state_lookup, 64);
+    u64vec el = {0};
+    size_t pos = 0; uint64_t idx = 0; const unsigned char *b, *e;
+    while (next_line(text, len, &pos, &b, &e)) {
+        int bad = parse_line(b, e, &el);
+        if (!bad) {
+            if (idx <= 2) {
+                if (el.n < 1) bad = 1;                       /* elements[0] out of bounds → panic */
+                else if (idx == 0) a->first_state_val = el.v[0];
+                else if (idx == 1) a->accepted_state_val = el.v[0];
+                else a->largest_state_val = el.v[0];
+            } else {
+                if (el.n < 3) bad = 1;
+                else map_insert(&a->state_lookup, (uint8_t)el.v[2], el.v[0], idx, el.v[1]); /* `as u8` truncates */
+            }
+        }
+        if (bad) {
+            if (err_line) *err_line = idx;
+            free(el.v); free(a->state_lookup.slots); free(a);
+            return B2R_ERR_PARSE;
+        }
+        idx++;
+    }
+    free(el.v);
+    *out = a;
+    return 0;
+}
+void orc_allstr_free(orc_allstr* a) { if (a) { free(a->state_lookup.slots); free(a); } }
+
+/* reference src/defs.rs:209-265 */
+int orc_substr_parse(const char* text, size_t len, orc_substr** out, uint64_t* err_line) {
+    orc_substr* s = (orc_substr*)calloc(1, sizeof(orc_substr));
+    set_init(&s->valid_state_transitions, 16);
+    u64vec el = {0};
+    size_t pos = 0; uint64_t idx = 0; const unsigned char *b, *e;
+    while (next_line(text, len, &pos, &b, &e)) {
+        int bad = parse_line(b, e, &el);
+        if (!bad) {
+            if (idx <= 2) {
+                if (el.n < 1) bad = 1;
+                else if (idx == 0) s->max_length = el.v[0];
+                else if (idx == 1) s->min_position = el.v[0];
+                else s->max_position = el.v[0];
+            } else if (idx == 3) {
+                s->start_states.n = 0; for (uint64_t i = 0; i < el.n; i++) vec_push(&s->start_states, el.v[i]);
+            } else if (idx == 4) {
+                s->end_states.n = 0; for (uint64_t i = 0; i < el.n; i++) vec_push(&s->end_states, el.v[i]);
+            } else {
+                if (el.n < 2) bad = 1; else set_insert(&s->valid_state_transitions, el.v[0], el.v[1]);
+            }
+        }
+        if (bad) {
+            if (err_line) *err_line = idx;
+            free(el.v); free(s->valid_state_transitions.slots); free(s->start_states.v); free(s->end_states.v); free(s);
+            return B2R_ERR_PARSE;
+        }
+        idx++;
+    }
+    free(el.v);
+    *out = s;
+    return 0;
+}
+void orc_substr_free(orc_substr* s) {
+    if (s) { free(s->valid_state_transitions.slots); free(s->start_states.v); free(s->end_states.v); free(s); }
+}
+
+static int vec_contains(const u64vec* v, uint64_t x) { /* Vec::contains: linear */
+    for (uint64_t i = 0; i < v->n; i++) if (v->v[i] == x) return 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t ch, cur, next, sid; } table_row;
+typedef struct { uint64_t sid, start, end; } endpoint_row;
+
+typedef struct {
+    const orc_allstr* allstr;
+    const orc_substr** substrs;
+    uint32_t n_substrs;
+    uint64_t substr_id_offset;
+    table_row* rows; uint64_t n_rows;            /* src/table.rs:101-122 */
+    endpoint_row* erows; uint64_t n_erows;       /* src/table.rs:129-193 */
+    /* tuple → first row index, for the multiplicity definition */
+    uint64_t* tuple_keys; uint64_t* tuple_vals; uint64_t tuple_cap;
+} orc_def;
+
+typedef struct orc_config {
+    orc_def defs[B2R_MAX_DEFS];
+    uint32_t n_defs;
+    uint64_t max_chars_size;
+} orc_config;
+
+static uint64_t tuple_hash(uint64_t ch, uint64_t cur, uint64_t next, uint64_t sid) {
+    return mix64(mix64(mix64(ch * 0x9E3779B97F4A7C15ULL + cur) + next) + sid);
+}
+static void tuple_put(orc_def* d, const table_row* r, uint64_t idx) {
+    uint64_t h = tuple_hash(r->ch, r->cur, r->next, r->sid) & (d->tuple_cap - 1);
+    while (d->tuple_vals[h] != UINT64_MAX) {
+        const table_row* o = &d->rows[d->tuple_vals[h]];
+        if (o->ch == r->ch && o->cur == r->cur && o->next == r->next && o->sid == r->sid) return; /* first row wins */
+        h = (h + 1) & (d->tuple_cap - 1);
+    }
+    d->tuple_vals[h] = idx;
+}
+static uint64_t tuple_find(const orc_def* d, uint64_t ch, uint64_t cur, uint64_t next, uint64_t sid) {
+    uint64_t h = tuple_hash(ch, cur, next, sid) & (d->tuple_cap - 1);
+    while (d->tuple_vals[h] != UINT64_MAX) {
+        const table_row* o = &d->rows[d->tuple_vals[h]];
+        if (o->ch == ch && o->cur == cur && o->next == next && o->sid == sid) return d->tuple_vals[h];
+        h = (h + 1) & (d->tuple_cap - 1);
+    }
+    return UINT64_MAX;
+}
+
+static int cmp_slot_line(const void* a, const void* b) {
+    const map_slot* x = *(const map_slot* const*)a; const map_slot* y = *(const map_slot* const*)b;
+    return (x->line_idx > y->line_idx) - (x->line_idx < y->line_idx);
+}
+
+/* RegexTableConfig::load, src/table.rs:61-198 */
+static void build_tables(orc_def* d) {
+    const orc_allstr* a = d->allstr;
+    uint64_t dummy_state = a->largest_state_val + 1;                                    /* :67 */
+    uint64_t n = a->state_lookup.len;
+    d->rows = (table_row*)malloc((n + 1) * sizeof(table_row));
+    d->rows[0] = (table_row){0, dummy_state, dummy_state, 0};                           /* :101 */
+    const map_slot** sorted = (const map_slot**)malloc((n ? n : 1) * sizeof(void*));
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < a->state_lookup.cap; i++) if (a->state_lookup.slots[i].used) sorted[k++] = &a->state_lookup.slots[i];
+    qsort(sorted, n, sizeof(void*), cmp_slot_line);                                     /* :103-108 */
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t substr_id = 0;
+        for (uint32_t j = 0; j < d->n_substrs; j++) {                                   /* :111-120 */
+            if (set_contains(&d->substrs[j]->valid_state_transitions, sorted[i]->state, sorted[i]->next)) {
+                substr_id = d->substr_id_offset + j; break;
+            }
+        }
+        d->rows[i + 1] = (table_row){sorted[i]->ch, sorted[i]->state, sorted[i]->next, substr_id};
+    }
+    free(sorted);
+    d->n_rows = n + 1;
+    uint64_t ne = 1;
+    for (uint32_t j = 0; j < d->n_substrs; j++) ne += d->substrs[j]->start_states.n + d->substrs[j]->end_states.n;
+    d->erows = (endpoint_row*)malloc(ne * sizeof(endpoint_row));
+    uint64_t off = 0;
+    d->erows[off++] = (endpoint_row){0, dummy_state, dummy_state};                      /* :130-148 */
+    for (uint32_t j = 0; j < d->n_substrs; j++) {
+        uint64_t substr_id = d->substr_id_offset + j;                                   /* :150 */
+        for (uint64_t s = 0; s < d->substrs[j]->start_states.n; s++) d->erows[off++] = (endpoint_row){substr_id, d->substrs[j]->start_states.v[s], dummy_state};
+        for (uint64_t s = 0; s < d->substrs[j]->end_states.n; s++) d->erows[off++] = (endpoint_row){substr_id, dummy_state, d->substrs[j]->end_states.v[s]};
+    }
+    d->n_erows = off;
+    d->tuple_cap = 16; while (d->tuple_cap < d->n_rows * 2) d->tuple_cap *= 2;
+    d->tuple_vals = (uint64_t*)malloc(d->tuple_cap * sizeof(uint64_t));
+    for (uint64_t i = 0; i < d->tuple_cap; i++) d->tuple_vals[i] = UINT64_MAX;
+    for (uint64_t i = 0; i < d->n_rows; i++) tuple_put(d, &d->rows[i], i);
+}
+
+int orc_config_new(const orc_allstr* const* allstr, const orc_substr* const* const* substrs, const uint32_t* n_substrs,
+                   uint32_t n_defs, uint64_t max_chars_size, orc_config** out) {
+    if (n_defs == 0 || n_defs > B2R_MAX_DEFS || max_chars_size == 0) return B2R_ERR_INVALID_ARG;
+    orc_config* c = (orc_config*)calloc(1, sizeof(orc_config));
+    c->n_defs = n_defs; c->max_chars_size = max_chars_size;
+    uint64_t substr_id_offset = 1;                                                      /* src/lib.rs:780 */
+    for (uint32_t d = 0; d < n_defs; d++) {
+        orc_def* df = &c->defs[d];
+        df->allstr = allstr[d];
+        df->n_substrs = n_substrs[d];
+        df->substrs = (const orc_substr**)malloc((n_substrs[d] ? n_substrs[d] : 1) * sizeof(void*));
+        for (uint32_t j = 0; j < n_substrs[d]; j++) df->substrs[j] = substrs[d][j];
+        df->substr_id_offset = substr_id_offset;
+        build_tables(df);
+        substr_id_offset += n_substrs[d];                                               /* src/table.rs:197 */
+    }
+    *out = c;
+    return 0;
+}
+void orc_config_free(orc_config* c) {
+    if (!c) return;
+    for (uint32_t d = 0; d < c->n_defs; d++) { free(c->defs[d].substrs); free(c->defs[d].rows); free(c->defs[d].erows); free(c->defs[d].tuple_vals); }
+    free(c);
+}
+uint64_t orc_table_num_rows(const orc_config* c, uint32_t d) { return c->defs[d].n_rows; }
+uint64_t orc_endpoint_num_rows(const orc_config* c, uint32_t d) { return c->defs[d].n_erows; }
+void orc_table_rows(const orc_config* c, uint32_t d, uint64_t* out4) { memcpy(out4, c->defs[d].rows, c->defs[d].n_rows * sizeof(table_row)); }
+void orc_endpoint_rows(const orc_config* c, uint32_t d, uint64_t* out3) { memcpy(out3, c->defs[d].erows, c->defs[d].n_erows * sizeof(endpoint_row)); }
+uint64_t orc_allstr_num_transitions(const orc_allstr* a) { return a->state_lookup.len; }
+uint64_t orc_allstr_header(const orc_allstr* a, int which) { return which == 0 ? a->first_state_val : which == 1 ? a->accepted_state_val : a->largest_state_val; }
+uint64_t orc_substr_num_transitions(const orc_substr* s) { return s->valid_state_transitions.len; }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* per-thread scratch: the reference allocates these vectors on every match_substrs call */
+typedef struct {
+    uint64_t cap;                 /* >= M+2 */
+    uint64_t* states[B2R_MAX_DEFS];
+    uint64_t* substr_ids[B2R_MAX_DEFS];
+    uint8_t* is_starts[B2R_MAX_DEFS];
+    uint8_t* is_ends[B2R_MAX_DEFS];
+    int64_t *sid_sum, *is_start_sum, *is_end_sum, *start_mask, *end_mask;
+    uint64_t* mult[B2R_MAX_DEFS];
+    uint64_t* emult[B2R_MAX_DEFS];
+} scratch;
+
+static void scratch_init(scratch* s, const orc_config* c, uint64_t max_len) {
+    uint64_t M = c->max_chars_size;
+    uint64_t cap = (M > max_len ? M : max_len) + 2;
+    s->cap = cap;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        s->states[d] = (uint64_t*)malloc(cap * 8); s->substr_ids[d] = (uint64_t*)malloc(cap * 8);
+        s->is_starts[d] = (uint8_t*)malloc(cap); s->is_ends[d] = (uint8_t*)malloc(cap);
+        s->mult[d] = (uint64_t*)calloc(c->defs[d].n_rows, 8);
+        s->emult[d] = (uint64_t*)calloc(2 * c->defs[d].n_erows, 8);
+    }
+    s->sid_sum = (int64_t*)malloc(cap * 8); s->is_start_sum = (int64_t*)malloc(cap * 8); s->is_end_sum = (int64_t*)malloc(cap * 8);
+    s->start_mask = (int64_t*)malloc(cap * 8); s->end_mask = (int64_t*)malloc(cap * 8);
+}
+static void scratch_free(scratch* s, const orc_config* c) {
+    for (uint32_t d = 0; d < c->n_defs; d++) { free(s->states[d]); free(s->substr_ids[d]); free(s->is_starts[d]); free(s->is_ends[d]); free(s->mult[d]); free(s->emult[d]); }
+    free(s->sid_sum); free(s->is_start_sum); free(s->is_end_sum); free(s->start_mask); free(s->end_mask);
+}
+
+static inline int64_t gate_select(int64_t a, int64_t b, int64_t sel) { return sel * (a - b) + b; } /* halo2-base FlexGate::select */
+
+/* One string: reference match_substrs (src/lib.rs:311-773), integer values only. */
+static void match_one(const orc_config* c, scratch* t, const uint8_t* characters, uint64_t len, uint64_t j,
+                      const b2r_outputs* o, int want_mult) {
+    const uint64_t M = c->max_chars_size;
+    const uint32_t D = c->n_defs;
+    b2r_string_status st; memset(&st, 0, sizeof st); st.err_pos = 0xFFFFFFFFu;
+
+    if (len + 1 > M) { /* len == M silently drops the final state; out of domain */
+        st.flags |= B2R_ST_TOO_LONG;
+        if (o->status) o->status[j] = st;
+        return;
+    }
+
+    /* derive_states, src/lib.rs:804-823 */
+    for (uint32_t d = 0; d < D; d++) {
+        const orc_allstr* a = c->defs[d].allstr;
+        uint64_t* states = t->states[d];
+        states[0] = a->first_state_val;
+        for (uint64_t c_idx = 0; c_idx < len; c_idx++) {
+            uint64_t state = states[c_idx];
+            const map_slot* next_state = map_get(&a->state_lookup, characters[c_idx], state);
+            if (!next_state) { /* panic!("The transition from {} by {} is invalid!", state, *char) */
+                st.flags |= B2R_ST_INVALID_TRANSITION;
+                st.err_pos = (uint32_t)c_idx; st.err_state = (uint32_t)state; st.err_byte = characters[c_idx]; st.err_def = (uint8_t)d;
+                if (o->status) o->status[j] = st;
+                return;
+            }
+            states[c_idx + 1] = next_state->next;
+        }
+    }
+    /* derive_substr_ids, src/lib.rs:825-845 */
+    for (uint32_t d = 0; d < D; d++) {
+        const orc_def* df = &c->defs[d];
+        for (uint64_t state_idx = 0; state_idx < len; state_idx++) {
+            t->substr_ids[d][state_idx] = 0;
+            for (uint32_t substr_idx = 0; substr_idx < df->n_substrs; substr_idx++) {
+                if (set_contains(&df->substrs[substr_idx]->valid_state_transitions, t->states[d][state_idx], t->states[d][state_idx + 1])) {
+                    t->substr_ids[d][state_idx] = df->substr_id_offset + substr_idx;
+                    break;
+                }
+            }
+        }
+    }
+    /* derive_is_start_end, src/lib.rs:847-888 */
+    for (uint32_t d = 0; d < D; d++) {
+        const orc_def* df = &c->defs[d];
+        for (uint64_t i = 0; i < len; i++) {
+            uint64_t substr_id = t->substr_ids[d][i];
+            if (substr_id == 0) { t->is_starts[d][i] = 0; continue; }
+            t->is_starts[d][i] = (uint8_t)vec_contains(&df->substrs[substr_id - df->substr_id_offset]->start_states, t->states[d][i]);
+        }
+        t->is_starts[d][len] = 0;                                                       /* :869 */
+        t->is_ends[d][0] = 0;                                                           /* :882 */
+        for (uint64_t i = 0; i < len; i++) {
+            uint64_t substr_id = t->substr_ids[d][i];
+            if (substr_id == 0) { t->is_ends[d][i + 1] = 0; continue; }
+            t->is_ends[d][i + 1] = (uint8_t)vec_contains(&df->substrs[substr_id - df->substr_id_offset]->end_states, t->states[d][i + 1]);
+        }
+    }
+
+    /* assigned_substr_ids (M), assigned_is_start / assigned_is_end (M+1): src/lib.rs:377-385 */
+    for (uint64_t i = 0; i <= M; i++) { t->sid_sum[i] = 0; t->is_start_sum[i] = 0; t->is_end_sum[i] = 0; }
+
+    for (uint32_t d = 0; d < D; d++) {
+        const orc_def* df = &c->defs[d];
+        const uint64_t dummy = df->allstr->largest_state_val + 1;
+        uint8_t* st8 = NULL; uint16_t* st16 = NULL;
+        if (o->states[d]) { if (dummy <= 255) st8 = (uint8_t*)o->states[d] + j * o->row_pitch; else st16 = (uint16_t*)o->states[d] + j * o->row_pitch; }
+        uint8_t* sid_out = o->substr_ids[d] ? o->substr_ids[d] + j * o->row_pitch : NULL;
+        uint8_t* se_out = o->start_enable[d] ? o->start_enable[d] + j * o->bitmap_pitch : NULL;
+        uint8_t* ee_out = o->end_enable[d] ? o->end_enable[d] + j * o->bitmap_pitch : NULL;
+        if (se_out) memset(se_out, 0, (M + 7) / 8);
+        if (ee_out) memset(ee_out, 0, (M + 7) / 8);
+        for (uint64_t idx = 0; idx < M; idx++) {
+            /* state/substr_id/is_start/is_end values per row: src/lib.rs:388-418 */
+            uint64_t state_val, substr_id_val; int is_start_val, is_end_val;
+            if (idx < len) {
+                state_val = t->states[d][idx]; substr_id_val = t->substr_ids[d][idx];
+                is_start_val = t->is_starts[d][idx]; is_end_val = t->is_ends[d][idx];
+            } else if (idx == len) {
+                state_val = t->states[d][idx]; substr_id_val = 0; is_start_val = t->is_starts[d][idx]; is_end_val = t->is_ends[d][idx];
+            } else {
+                state_val = dummy; substr_id_val = 0; is_start_val = 0; is_end_val = 0;
+            }
+            int64_t enable = idx < len ? 1 : 0;                                         /* :339-348 */
+            if (st8) st8[idx] = (uint8_t)state_val;
+            if (st16) st16[idx] = (uint16_t)state_val;
+            if (sid_out) sid_out[idx] = (uint8_t)substr_id_val;
+            t->sid_sum[idx] += (int64_t)substr_id_val;                                  /* :467-471 */
+            int64_t start_enable = enable * is_start_val;                               /* :483-493 */
+            if (se_out && start_enable) se_out[idx >> 3] |= (uint8_t)(1u << (idx & 7));
+            t->is_start_sum[idx] += is_start_val;                                       /* :494-498 */
+            /* the end loop (:501-519) runs idx in 0..M-1 and reads is_end_values[idx+1] */
+            if (idx >= 1) t->is_end_sum[idx] += is_end_val;                             /* assigned_is_end[idx], idx in 1..M-1 */
+            if (idx + 1 < M) {
+                int next_is_end = (idx + 1 <= len) ? t->is_ends[d][idx + 1] : 0;
+                int64_t end_enable = enable * next_is_end;
+                if (ee_out && end_enable) ee_out[idx >> 3] |= (uint8_t)(1u << (idx & 7));
+            }
+            if (want_mult) {
+                /* lookup tuples, src/lib.rs:218-232, 247-257, 273-283 */
+                uint64_t next_val = (idx + 1 < M) ? ((idx + 1 <= len) ? t->states[d][idx + 1] : dummy) : dummy; /* Rotation::next of the last row is never enabled */
+                uint64_t tc = enable ? characters[idx] : 0, tcur = enable ? state_val : dummy, tnext = enable ? next_val : dummy, tsid = enable ? substr_id_val : 0;
+                uint64_t r = tuple_find(df, tc, tcur, tnext, tsid);
+                if (r != UINT64_MAX) t->mult[d][r]++;
+                uint64_t s_sid = start_enable ? substr_id_val : 0, s_st = start_enable ? state_val : dummy;
+                int64_t end_enable = (idx + 1 < M) ? enable * ((idx + 1 <= len) ? t->is_ends[d][idx + 1] : 0) : 0;
+                uint64_t e_sid = end_enable ? substr_id_val : 0, e_st = end_enable ? next_val : dummy;
+                for (uint64_t r2 = 0; r2 < df->n_erows; r2++) if (df->erows[r2].sid == s_sid && df->erows[r2].start == s_st && df->erows[r2].end == dummy) { t->emult[d][r2]++; break; }
+                for (uint64_t r2 = 0; r2 < df->n_erows; r2++) if (df->erows[r2].sid == e_sid && df->erows[r2].start == dummy && df->erows[r2].end == e_st) { t->emult[d][df->n_erows + r2]++; break; }
+            }
+        }
+        /* accept rule, src/lib.rs:427-457: the row where enable drops 1→0 (row len; pre_flag=1 at row 0) */
+        if (t->states[d][len] == df->allstr->accepted_state_val) st.flags |= B2R_ST_ACCEPTED(d);
+    }
+
+    int overlap = 0;
+    for (uint64_t i = 0; i <= M; i++) if (t->is_start_sum[i] > 1 || t->is_end_sum[i] > 1) overlap = 1;
+    if (overlap) st.flags |= B2R_ST_OVERLAP;
+
+    /* start_mask, src/lib.rs:598-645 */
+    int64_t last_start_mask = 0;
+    for (uint64_t idx = 0; idx < M; idx++) {
+        int64_t pre_substr_id = idx == 0 ? 0 : t->sid_sum[idx - 1];
+        int64_t is_eq = pre_substr_id == t->sid_sum[idx];
+        int64_t is_changed = 1 - is_eq;
+        int64_t is_set = t->is_start_sum[idx] * is_changed;
+        int64_t is_reset = ((1 - t->is_start_sum[idx]) * t->is_end_sum[idx]) * is_changed;
+        int64_t new_mask = gate_select(1, last_start_mask, is_set);
+        new_mask = gate_select(0, new_mask, is_reset);
+        t->start_mask[idx] = new_mask; last_start_mask = new_mask;
+    }
+    /* end_mask, src/lib.rs:663-714 (built reversed, then reversed) */
+    int64_t last_end_mask = 0;
+    for (uint64_t idx = 0; idx < M; idx++) {
+        int64_t pre_substr_id = idx == 0 ? 0 : t->sid_sum[M - idx];
+        int64_t is_eq = pre_substr_id == t->sid_sum[M - 1 - idx];
+        int64_t is_changed = 1 - is_eq;
+        int64_t is_set = t->is_end_sum[M - idx] * is_changed;
+        int64_t is_reset = ((1 - t->is_end_sum[M - idx]) * t->is_start_sum[M - idx]) * is_changed;
+        int64_t new_mask = gate_select(1, last_end_mask, is_set);
+        new_mask = gate_select(0, new_mask, is_reset);
+        t->end_mask[M - 1 - idx] = new_mask; last_end_mask = new_mask;
+    }
+    /* masked outputs, src/lib.rs:740-764 */
+    uint8_t* mc = o->masked_chars ? o->masked_chars + j * o->row_pitch : NULL;
+    uint8_t* ms = o->masked_substr_ids ? o->masked_substr_ids + j * o->row_pitch : NULL;
+    b2r_substr_record* rec = o->records ? o->records + j * (uint64_t)o->max_records : NULL;
+    uint8_t* cb = o->compact_bytes ? o->compact_bytes + j * (uint64_t)o->compact_pitch : NULL;
+    uint32_t n_rec = 0, n_cmp = 0; int in_run = 0; int64_t run_sid = 0;
+    for (uint64_t idx = 0; idx < M; idx++) {
+        int64_t mask = t->start_mask[idx] * t->end_mask[idx];
+        int64_t ch = idx < len ? characters[idx] : 0;
+        int64_t masked_char = mask * ch, masked_substr_id = mask * t->sid_sum[idx];
+        if (mc) mc[idx] = (uint8_t)masked_char;
+        if (ms) ms[idx] = (uint8_t)masked_substr_id;
+        /* compact records (defined by this repo, include/b2r.h): maximal runs of mask=1 with a constant id sum */
+        if (!overlap && mask == 1) {
+            if (!in_run || run_sid != t->sid_sum[idx]) {
+                if (rec && n_rec < o->max_records) rec[n_rec] = (b2r_substr_record){(uint32_t)idx, 0, (uint32_t)t->sid_sum[idx], n_cmp};
+                n_rec++; in_run = 1; run_sid = t->sid_sum[idx];
+            }
+            if (rec && n_rec <= o->max_records) rec[n_rec - 1].len++;
+            if (cb && n_cmp < o->compact_pitch) cb[n_cmp] = (uint8_t)ch;
+            n_cmp++;
+        } else in_run = 0;
+    }
+    st.n_records = n_rec; st.n_compact = n_cmp;
+    if (o->records && n_rec > o->max_records) st.flags |= B2R_ST_RECORDS_TRUNCATED;
+    if (o->compact_bytes && n_cmp > o->compact_pitch) st.flags |= B2R_ST_COMPACT_TRUNCATED;
+    if (o->status) o->status[j] = st;
+}
+
+typedef struct {
+    const orc_config* c; const uint8_t* bytes; const uint64_t* offsets; uint64_t j0, j1; const b2r_outputs* o;
+    scratch t; int want_mult; uint64_t max_len;
+} job;
+static void* worker(void* p) {
+    job* jb = (job*)p;
+    scratch_init(&jb->t, jb->c, jb->max_len);
+    for (uint64_t j = jb->j0; j < jb->j1; j++)
+        match_one(jb->c, &jb->t, jb->bytes + jb->offsets[j], jb->offsets[j + 1] - jb->offsets[j], j, jb->o, jb->want_mult);
+    return NULL;
+}
+
+/* Batch driver (host pointers in *o, same layout as the product's b2r_outputs).  nthreads partitions the strings
+ * contiguously; the reference itself is single-threaded. */
+int orc_match_batch(const orc_config* c, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, const b2r_outputs* o,
+                    int nthreads, b2r_batch_status* result) {
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > n && n > 0) nthreads = (int)n;
+    int want_mult = 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) if (o->mult[d] || o->endpoint_mult[d]) want_mult = 1;
+    uint64_t M = c->max_chars_size;
+    job* jobs = (job*)calloc(nthreads, sizeof(job));
+    pthread_t* th = (pthread_t*)calloc(nthreads, sizeof(pthread_t));
+    for (int k = 0; k < nthreads; k++) {
+        jobs[k] = (job){c, bytes, offsets, n * k / nthreads, n * (k + 1) / nthreads, o, {0}, want_mult, M};
+        if (nthreads == 1) worker(&jobs[k]); else pthread_create(&th[k], NULL, worker, &jobs[k]);
+    }
+    if (nthreads > 1) for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        int acc = (o->flags & B2R_OUT_ACCUMULATE_MULT) != 0;
+        if (o->mult[d]) {
+            if (!acc) memset(o->mult[d], 0, c->defs[d].n_rows * 8);
+            for (int k = 0; k < nthreads; k++) for (uint64_t r = 0; r < c->defs[d].n_rows; r++) o->mult[d][r] += jobs[k].t.mult[d][r];
+        }
+        if (o->endpoint_mult[d]) {
+            if (!acc) memset(o->endpoint_mult[d], 0, 2 * c->defs[d].n_erows * 8);
+            for (int k = 0; k < nthreads; k++) for (uint64_t r = 0; r < 2 * c->defs[d].n_erows; r++) o->endpoint_mult[d][r] += jobs[k].t.emult[d][r];
+        }
+    }
+    for (int k = 0; k < nthreads; k++) scratch_free(&jobs[k].t, c);
+    free(jobs); free(th);
+    if (result) {
+        memset(result, 0, sizeof *result);
+        uint64_t n_overlap = 0;
+        if (o->status) for (uint64_t j = 0; j < n; j++) {
+            const b2r_string_status* s = &o->status[j];
+            if (s->flags & B2R_ST_OVERLAP) n_overlap++;
+            if (result->code == 0 && (s->flags & (B2R_ST_INVALID_TRANSITION | B2R_ST_TOO_LONG))) {
+                result->code = (s->flags & B2R_ST_TOO_LONG) ? B2R_ERR_TOO_LONG : B2R_ERR_INVALID_TRANSITION;
+                result->string_idx = j; result->pos = s->err_pos; result->state = s->err_state; result->byte = s->err_byte; result->def = s->err_def;
+            }
+        }
+        result->n_overlap_lo = (uint32_t)n_overlap;
+    }
+    return 0;
+}
