@@ -1,0 +1,518 @@
+// extern "C" boundary (include/b2r.h): handles, table queries, the batch entry points.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b2r.h"
+#include "defs.hpp"
+#include "kernels.cuh"
+
+using namespace b2r;
+
+struct b2r_allstr { AllstrDef def; };
+struct b2r_substr { SubstrDef def; };
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                   \
+            return B2R_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return B2R_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CUDA_TRY(cudaMalloc(&p, n));
+        cap = n;
+        return B2R_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DevDef {
+    uint8_t* byte_class = nullptr;
+    uint32_t* trans = nullptr;
+    uint32_t *row_bin = nullptr, *erow_start_bin = nullptr, *erow_end_bin = nullptr;
+    unsigned long long *hist = nullptr, *ep_start = nullptr, *ep_end = nullptr;  // inside cfg->scratch
+};
+
+}  // namespace
+
+struct b2r_config {
+    int device = -1;             // -1: host-only handle (table queries), no matching
+    uint64_t max_chars = 0;
+    uint32_t n_defs = 0;
+    PackedDef packed[B2R_MAX_DEFS];
+    DevDef dev[B2R_MAX_DEFS];
+    void* tables = nullptr;      // one allocation holding every constant table
+    void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
+    size_t scratch_bytes = 0;
+    b2r_batch_status* d_batch_status = nullptr;
+    WalkParams last = {};
+    bool have_last = false;
+    uint32_t last_launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // staging for the host-pointer entry point
+    DevBuf ws_bytes, ws_offsets, ws_cols;
+    cudaStream_t host_stream = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int upload_tables(b2r_config* c) {
+    size_t total = 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const PackedDef& pd = c->packed[d];
+        total += align_up(256, 256) + align_up(pd.trans.size() * 4, 256) + align_up(pd.row_bin.size() * 4, 256) +
+                 2 * align_up(pd.erows.size() * 4, 256);
+    }
+    CUDA_TRY(cudaMalloc(&c->tables, total));
+    unsigned char* base = (unsigned char*)c->tables;
+    size_t off = 0;
+    auto put = [&](const void* src, size_t n) -> void* {
+        void* dst = base + off;
+        cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+        off += align_up(n, 256);
+        return dst;
+    };
+    size_t scratch = align_up(sizeof(BatchCounters), 256);
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const PackedDef& pd = c->packed[d];
+        c->dev[d].byte_class = (uint8_t*)put(pd.byte_class.data(), 256);
+        c->dev[d].trans = (uint32_t*)put(pd.trans.data(), pd.trans.size() * 4);
+        c->dev[d].row_bin = (uint32_t*)put(pd.row_bin.data(), pd.row_bin.size() * 4);
+        c->dev[d].erow_start_bin = (uint32_t*)put(pd.erow_start_bin.data(), pd.erows.size() * 4);
+        c->dev[d].erow_end_bin = (uint32_t*)put(pd.erow_end_bin.data(), pd.erows.size() * 4);
+        scratch += align_up((size_t)256 * pd.num_states * 8, 256) + 2 * align_up((size_t)std::max<uint32_t>(pd.num_substrs, 1) * pd.num_states * 8, 256);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMalloc(&c->scratch, scratch));
+    c->scratch_bytes = scratch;
+    unsigned char* sb = (unsigned char*)c->scratch;
+    size_t so = align_up(sizeof(BatchCounters), 256);
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const PackedDef& pd = c->packed[d];
+        c->dev[d].hist = (unsigned long long*)(sb + so); so += align_up((size_t)256 * pd.num_states * 8, 256);
+        const size_t ep = align_up((size_t)std::max<uint32_t>(pd.num_substrs, 1) * pd.num_states * 8, 256);
+        c->dev[d].ep_start = (unsigned long long*)(sb + so); so += ep;
+        c->dev[d].ep_end = (unsigned long long*)(sb + so); so += ep;
+    }
+    CUDA_TRY(cudaMalloc((void**)&c->d_batch_status, sizeof(b2r_batch_status)));
+    return B2R_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_outputs(const b2r_config* c, const b2r_outputs* o, bool check_ptrs) {
+    const uint64_t M = c->max_chars;
+    if (o->row_pitch < M || o->row_pitch % 16) { set_error("row_pitch %llu must be >= max_chars_size and a multiple of 16", (unsigned long long)o->row_pitch); return B2R_ERR_ALIGNMENT; }
+    if (o->bitmap_pitch < (M + 7) / 8 || o->bitmap_pitch % 4) { set_error("bitmap_pitch %llu must be >= ceil(M/8) and a multiple of 4", (unsigned long long)o->bitmap_pitch); return B2R_ERR_ALIGNMENT; }
+    if (!check_ptrs) return B2R_OK;
+    bool ok = aligned16(o->masked_chars) && aligned16(o->masked_substr_ids);
+    for (uint32_t d = 0; d < c->n_defs; d++)
+        ok = ok && aligned16(o->states[d]) && aligned16(o->substr_ids[d]) && aligned16(o->start_enable[d]) && aligned16(o->end_enable[d]);
+    if (!ok) { set_error("output columns must be 16-byte aligned"); return B2R_ERR_ALIGNMENT; }
+    return B2R_OK;
+}
+
+void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+                      const b2r_outputs* o, uint64_t max_chars) {
+    memset(&p, 0, sizeof p);
+    p.bytes = d_bytes; p.offsets = d_offsets; p.n_strings = n; p.total_bytes = total_bytes;
+    p.row_pitch = o->row_pitch; p.bitmap_pitch = o->bitmap_pitch;
+    p.max_chars = (uint32_t)max_chars; p.n_defs = c->n_defs;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const PackedDef& pd = c->packed[d];
+        DefDev& dd = p.def[d];
+        dd.byte_class = c->dev[d].byte_class; dd.trans = c->dev[d].trans;
+        dd.num_states = pd.num_states; dd.num_classes = pd.num_classes; dd.first_state = pd.first_state;
+        dd.accepted_state = pd.accepted_state; dd.sid_offset = pd.substr_id_offset; dd.num_substrs = pd.num_substrs;
+        dd.hist = c->dev[d].hist; dd.ep_start = c->dev[d].ep_start; dd.ep_end = c->dev[d].ep_end;
+        dd.states = o->states[d]; dd.substr_ids = o->substr_ids[d]; dd.start_enable = o->start_enable[d]; dd.end_enable = o->end_enable[d];
+    }
+    p.masked_chars = o->masked_chars; p.masked_substr_ids = o->masked_substr_ids;
+    p.status = o->status; p.records = o->records; p.compact_bytes = o->compact_bytes;
+    p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
+    p.counters = (BatchCounters*)c->scratch;
+    p.n_tiles = (uint32_t)((n + 31) / 32);
+    for (uint32_t d = 0; d < c->n_defs; d++) p.want_hist |= (o->mult[d] != nullptr);
+}
+
+int enqueue_finalize(b2r_config* c, const b2r_outputs* o, uint64_t n, uint64_t max_chars, cudaStream_t st) {
+    FinalizeParams f;
+    memset(&f, 0, sizeof f);
+    f.n_defs = c->n_defs; f.accumulate = (o->flags & B2R_OUT_ACCUMULATE_MULT) ? 1 : 0;
+    f.n_rows_total = n * max_chars; f.counters = (const BatchCounters*)c->scratch;
+    bool any = false;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        auto& fd = f.def[d];
+        fd.hist = c->dev[d].hist; fd.row_bin = c->dev[d].row_bin; fd.n_rows = (uint32_t)c->packed[d].rows.size();
+        fd.ep_start = c->dev[d].ep_start; fd.ep_end = c->dev[d].ep_end;
+        fd.erow_start_bin = c->dev[d].erow_start_bin; fd.erow_end_bin = c->dev[d].erow_end_bin; fd.n_erows = (uint32_t)c->packed[d].erows.size();
+        fd.mult = (unsigned long long*)o->mult[d]; fd.endpoint_mult = (unsigned long long*)o->endpoint_mult[d];
+        any = any || fd.mult || fd.endpoint_mult;
+    }
+    if (!any) return B2R_OK;
+    c->last_launches++;
+    return launch_finalize(f, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2r_last_error(void) { return get_error(); }
+const char* b2r_version(void) { return "b2r 0.1 (sm_100a)"; }
+
+// ---- AllstrRegexDef ------------------------------------------------------------------------------------------------
+int b2r_allstr_parse(const char* text, size_t len, b2r_allstr** out, uint64_t* err_line) {
+    if (!out || (!text && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    std::unique_ptr<b2r_allstr> a(new (std::nothrow) b2r_allstr);
+    int rc = parse_allstr(text, len, a->def, err_line);
+    if (rc) return rc;
+    *out = a.release();
+    return B2R_OK;
+}
+int b2r_allstr_read_from_text(const char* path, b2r_allstr** out, uint64_t* err_line) {
+    std::string s;
+    int rc = read_file(path, s);
+    if (rc) return rc;
+    return b2r_allstr_parse(s.data(), s.size(), out, err_line);
+}
+void b2r_allstr_free(b2r_allstr* a) { delete a; }
+uint64_t b2r_allstr_first_state_val(const b2r_allstr* a) { return a->def.first_state_val; }
+uint64_t b2r_allstr_accepted_state_val(const b2r_allstr* a) { return a->def.accepted_state_val; }
+uint64_t b2r_allstr_largest_state_val(const b2r_allstr* a) { return a->def.largest_state_val; }
+uint64_t b2r_allstr_num_transitions(const b2r_allstr* a) { return a->def.state_lookup.size(); }
+int b2r_allstr_lookup(const b2r_allstr* a, uint8_t ch, uint64_t state, uint64_t* line_idx, uint64_t* next) {
+    auto it = a->def.state_lookup.find({state, ch});
+    if (it == a->def.state_lookup.end()) return 0;
+    if (line_idx) *line_idx = it->second.first;
+    if (next) *next = it->second.second;
+    return 1;
+}
+int b2r_allstr_entries(const b2r_allstr* a, uint64_t* out4, uint64_t capacity_rows) {
+    const auto v = a->def.in_table_order();
+    if (capacity_rows < v.size()) { set_error("capacity too small"); return B2R_ERR_INVALID_ARG; }
+    for (size_t i = 0; i < v.size(); i++) { out4[4 * i] = v[i].ch; out4[4 * i + 1] = v[i].cur; out4[4 * i + 2] = v[i].next; out4[4 * i + 3] = v[i].line_idx; }
+    return B2R_OK;
+}
+
+// ---- SubstrRegexDef ------------------------------------------------------------------------------------------------
+int b2r_substr_parse(const char* text, size_t len, b2r_substr** out, uint64_t* err_line) {
+    if (!out || (!text && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    std::unique_ptr<b2r_substr> s(new (std::nothrow) b2r_substr);
+    int rc = parse_substr(text, len, s->def, err_line);
+    if (rc) return rc;
+    *out = s.release();
+    return B2R_OK;
+}
+int b2r_substr_read_from_text(const char* path, b2r_substr** out, uint64_t* err_line) {
+    std::string s;
+    int rc = read_file(path, s);
+    if (rc) return rc;
+    return b2r_substr_parse(s.data(), s.size(), out, err_line);
+}
+int b2r_substr_new(uint64_t max_length, uint64_t min_position, uint64_t max_position, const uint64_t* pairs, uint64_t n_pairs,
+                   const uint64_t* start_states, uint64_t n_start, const uint64_t* end_states, uint64_t n_end, b2r_substr** out) {
+    if (!out) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    std::unique_ptr<b2r_substr> s(new (std::nothrow) b2r_substr);
+    s->def.max_length = max_length; s->def.min_position = min_position; s->def.max_position = max_position;
+    for (uint64_t i = 0; i < n_pairs; i++) s->def.valid_state_transitions.insert({pairs[2 * i], pairs[2 * i + 1]});
+    s->def.start_states.assign(start_states, start_states + n_start);
+    s->def.end_states.assign(end_states, end_states + n_end);
+    *out = s.release();
+    return B2R_OK;
+}
+void b2r_substr_free(b2r_substr* s) { delete s; }
+uint64_t b2r_substr_max_length(const b2r_substr* s) { return s->def.max_length; }
+uint64_t b2r_substr_min_position(const b2r_substr* s) { return s->def.min_position; }
+uint64_t b2r_substr_max_position(const b2r_substr* s) { return s->def.max_position; }
+uint64_t b2r_substr_num_transitions(const b2r_substr* s) { return s->def.valid_state_transitions.size(); }
+uint64_t b2r_substr_num_start_states(const b2r_substr* s) { return s->def.start_states.size(); }
+uint64_t b2r_substr_num_end_states(const b2r_substr* s) { return s->def.end_states.size(); }
+int b2r_substr_transitions(const b2r_substr* s, uint64_t* out2, uint64_t capacity) {
+    if (capacity < s->def.valid_state_transitions.size()) { set_error("capacity too small"); return B2R_ERR_INVALID_ARG; }
+    size_t i = 0;
+    for (const auto& pr : s->def.valid_state_transitions) { out2[2 * i] = pr.first; out2[2 * i + 1] = pr.second; i++; }
+    return B2R_OK;
+}
+int b2r_substr_start_states(const b2r_substr* s, uint64_t* out, uint64_t capacity) {
+    if (capacity < s->def.start_states.size()) { set_error("capacity too small"); return B2R_ERR_INVALID_ARG; }
+    std::copy(s->def.start_states.begin(), s->def.start_states.end(), out);
+    return B2R_OK;
+}
+int b2r_substr_end_states(const b2r_substr* s, uint64_t* out, uint64_t capacity) {
+    if (capacity < s->def.end_states.size()) { set_error("capacity too small"); return B2R_ERR_INVALID_ARG; }
+    std::copy(s->def.end_states.begin(), s->def.end_states.end(), out);
+    return B2R_OK;
+}
+int b2r_substr_contains(const b2r_substr* s, uint64_t cur, uint64_t next) { return s->def.valid_state_transitions.count({cur, next}) ? 1 : 0; }
+
+// ---- RegexVerifyConfig -----------------------------------------------------------------------------------------------
+int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* const* substrs, const uint32_t* n_substrs, uint32_t n_defs,
+                   uint64_t max_chars_size, int device, b2r_config** out) {
+    if (!allstr || !n_substrs || !out || n_defs == 0) { set_error("null / empty argument"); return B2R_ERR_INVALID_ARG; }
+    if (n_defs > B2R_MAX_DEFS) { set_error("%u regex defs: at most %d are supported", n_defs, B2R_MAX_DEFS); return B2R_ERR_UNSUPPORTED; }
+    if (max_chars_size == 0 || max_chars_size > 0xFFFFFFF0ull) { set_error("max_chars_size out of range"); return B2R_ERR_INVALID_ARG; }
+    std::unique_ptr<b2r_config> c(new (std::nothrow) b2r_config);
+    c->n_defs = n_defs; c->max_chars = max_chars_size; c->device = device;
+    uint32_t offset = 1;  // src/lib.rs:780, 827
+    uint64_t max_sum = 0;
+    for (uint32_t d = 0; d < n_defs; d++) {
+        std::vector<const SubstrDef*> subs;
+        for (uint32_t k = 0; k < n_substrs[d]; k++) subs.push_back(&substrs[d][k]->def);
+        int rc = pack_def(allstr[d]->def, subs, offset, c->packed[d]);
+        if (rc) return rc;
+        if (n_substrs[d]) max_sum += offset + n_substrs[d] - 1;
+        offset += n_substrs[d];  // src/table.rs:197
+    }
+    if (max_sum > 255) { set_error("sum of the largest substr ids over defs is %llu > 255", (unsigned long long)max_sum); return B2R_ERR_UNSUPPORTED; }
+    if (device >= 0) {
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device >= n_dev) {
+            set_error("CUDA device %d is not available (%d devices); this library has no CPU fallback", device, n_dev);
+            return B2R_ERR_CUDA;
+        }
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return B2R_ERR_CUDA; }
+        DeviceGuard g(device);
+        if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B2R_ERR_CUDA; }
+        int rc = upload_tables(c.get());
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    *out = c.release();
+    return B2R_OK;
+}
+
+void b2r_config_free(b2r_config* c) {
+    if (!c) return;
+    if (c->device >= 0) {
+        DeviceGuard g(c->device);
+        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
+        c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
+        if (c->host_stream) cudaStreamDestroy(c->host_stream);
+        for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    }
+    delete c;
+}
+uint32_t b2r_config_num_defs(const b2r_config* c) { return c->n_defs; }
+uint64_t b2r_config_max_chars_size(const b2r_config* c) { return c->max_chars; }
+int b2r_config_device(const b2r_config* c) { return c->device; }
+uint32_t b2r_config_state_width(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].state_width : 0; }
+uint64_t b2r_config_dummy_state(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].num_states : 0; }
+uint32_t b2r_config_substr_id_offset(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].substr_id_offset : 0; }
+uint32_t b2r_config_num_byte_classes(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].num_classes : 0; }
+uint64_t b2r_config_recommended_row_pitch(const b2r_config* c) { return align_up(c->max_chars, 32); }
+uint64_t b2r_config_recommended_bitmap_pitch(const b2r_config* c) { return align_up((c->max_chars + 7) / 8, 32); }
+
+uint64_t b2r_table_num_rows(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].rows.size() : 0; }
+int b2r_table_rows(const b2r_config* c, uint32_t d, uint64_t* out4, uint64_t capacity_rows) {
+    if (d >= c->n_defs || capacity_rows < c->packed[d].rows.size()) { set_error("bad def index / capacity"); return B2R_ERR_INVALID_ARG; }
+    const auto& rows = c->packed[d].rows;
+    for (size_t i = 0; i < rows.size(); i++) { out4[4 * i] = rows[i].ch; out4[4 * i + 1] = rows[i].cur; out4[4 * i + 2] = rows[i].next; out4[4 * i + 3] = rows[i].sid; }
+    return B2R_OK;
+}
+uint64_t b2r_endpoint_num_rows(const b2r_config* c, uint32_t d) { return d < c->n_defs ? c->packed[d].erows.size() : 0; }
+int b2r_endpoint_rows(const b2r_config* c, uint32_t d, uint64_t* out3, uint64_t capacity_rows) {
+    if (d >= c->n_defs || capacity_rows < c->packed[d].erows.size()) { set_error("bad def index / capacity"); return B2R_ERR_INVALID_ARG; }
+    const auto& rows = c->packed[d].erows;
+    for (size_t i = 0; i < rows.size(); i++) { out3[3 * i] = rows[i].sid; out3[3 * i + 1] = rows[i].start; out3[3 * i + 2] = rows[i].end; }
+    return B2R_OK;
+}
+
+// ---- the hot call ------------------------------------------------------------------------------------------------------
+static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+                            const b2r_outputs* o, uint64_t max_chars, cudaStream_t st) {
+    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
+    if (!o || (n && (!d_bytes && total_bytes)) || (n && !d_offsets)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (!aligned16(d_bytes)) { set_error("bytes must be 16-byte aligned"); return B2R_ERR_ALIGNMENT; }
+    int rc = check_outputs(c, o, true);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
+    c->last_launches = 0;
+    CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none
+    WalkParams& p = c->last;
+    fill_walk_params(c, p, d_bytes, d_offsets, n, total_bytes, o, max_chars);
+    c->have_last = true;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
+    if (n) {
+        bool wide = false;
+        for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
+        for (uint32_t d = 0; d < c->n_defs; d++)
+            if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
+        rc = launch_walk(p, wide, st, nullptr);
+        if (rc) return rc;
+        c->last_launches++;
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
+    rc = enqueue_finalize(c, o, n, max_chars, st);
+    if (rc) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    return B2R_OK;
+}
+
+int b2r_match_batch(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+                    const b2r_outputs* d_out, void* cuda_stream) {
+    if (!c) { set_error("null config"); return B2R_ERR_INVALID_ARG; }
+    return match_batch_impl(c, d_bytes, d_offsets, n, total_bytes, d_out, c->max_chars, (cudaStream_t)cuda_stream);
+}
+
+int b2r_batch_result(b2r_config* c, void* cuda_stream, b2r_batch_status* out) {
+    if (!c || c->device < 0 || !c->have_last) { set_error("no batch has been enqueued on this handle"); return B2R_ERR_INVALID_ARG; }
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    BatchCounters h;
+    CUDA_TRY(cudaMemcpy(&h, c->scratch, sizeof h, cudaMemcpyDeviceToHost));
+    b2r_batch_status r;
+    memset(&r, 0, sizeof r);
+    r.n_overlap_lo = (uint32_t)h.n_overlap;
+    if (h.first_bad != ~0ull) {
+        int rc = launch_diagnose(c->last, h.first_bad, c->d_batch_status, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(&r, c->d_batch_status, sizeof r, cudaMemcpyDeviceToHost));
+        if (r.code == B2R_ERR_INVALID_TRANSITION)
+            set_error("The transition from %u by %u is invalid! (string %llu, position %u, def %u)", r.state, (unsigned)r.byte,
+                      (unsigned long long)r.string_idx, r.pos, (unsigned)r.def);
+        else if (r.code == B2R_ERR_TOO_LONG)
+            set_error("string %llu is longer than max_chars_size-1", (unsigned long long)r.string_idx);
+    }
+    if (out) *out = r;
+    return r.code;
+}
+
+// ---- host-pointer entry point ----------------------------------------------------------------------------------------
+int b2r_match_batch_host(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets, uint64_t n, const b2r_outputs* ho,
+                         b2r_batch_status* result) {
+    if (!c || !ho || (n && !h_offsets)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
+    int rc = check_outputs(c, ho, false);  // same pitches are used on the device; host pointer alignment is irrelevant
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->host_stream;
+    const uint64_t total = n ? h_offsets[n] : 0;
+    const uint64_t base = n ? h_offsets[0] : 0;
+    if (total < base) { set_error("offsets must be non-decreasing"); return B2R_ERR_INVALID_ARG; }
+    const uint64_t nbytes = total - base;
+    if ((rc = c->ws_bytes.reserve(align_up(nbytes + 16, 256)))) return rc;
+    if ((rc = c->ws_offsets.reserve((n + 1) * 8))) return rc;
+    // device columns, same layout as the host ones
+    const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
+    size_t need = 0;
+    auto slot = [&](size_t bytes) { size_t o = need; need += align_up(bytes, 256); return o; };
+    struct Copy { size_t off; void* host; size_t bytes; };
+    std::vector<Copy> copies;
+    b2r_outputs dout = *ho;
+    size_t off_states[B2R_MAX_DEFS], off_sid[B2R_MAX_DEFS], off_se[B2R_MAX_DEFS], off_ee[B2R_MAX_DEFS], off_mult[B2R_MAX_DEFS], off_em[B2R_MAX_DEFS];
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const size_t w = c->packed[d].state_width;
+        off_states[d] = ho->states[d] ? slot(n * rp * w) : 0;
+        off_sid[d] = ho->substr_ids[d] ? slot(n * rp) : 0;
+        off_se[d] = ho->start_enable[d] ? slot(n * bp) : 0;
+        off_ee[d] = ho->end_enable[d] ? slot(n * bp) : 0;
+        off_mult[d] = ho->mult[d] ? slot(c->packed[d].rows.size() * 8) : 0;
+        off_em[d] = ho->endpoint_mult[d] ? slot(c->packed[d].erows.size() * 16) : 0;
+    }
+    const size_t off_mc = ho->masked_chars ? slot(n * rp) : 0, off_ms = ho->masked_substr_ids ? slot(n * rp) : 0;
+    const size_t off_st = ho->status ? slot(n * sizeof(b2r_string_status)) : 0;
+    const size_t off_rec = ho->records ? slot(n * (size_t)ho->max_records * sizeof(b2r_substr_record)) : 0;
+    const size_t off_cb = ho->compact_bytes ? slot(n * (size_t)ho->compact_pitch) : 0;
+    if ((rc = c->ws_cols.reserve(need + 256))) return rc;
+    unsigned char* cb = (unsigned char*)c->ws_cols.p;
+    auto bind = [&](void* host, size_t off, size_t bytes) -> void* {
+        if (!host) return nullptr;
+        copies.push_back({off, host, bytes});
+        return cb + off;
+    };
+    const bool acc = (ho->flags & B2R_OUT_ACCUMULATE_MULT) != 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        const size_t w = c->packed[d].state_width;
+        dout.states[d] = bind(ho->states[d], off_states[d], n * rp * w);
+        dout.substr_ids[d] = (uint8_t*)bind(ho->substr_ids[d], off_sid[d], n * rp);
+        dout.start_enable[d] = (uint8_t*)bind(ho->start_enable[d], off_se[d], n * bp);
+        dout.end_enable[d] = (uint8_t*)bind(ho->end_enable[d], off_ee[d], n * bp);
+        dout.mult[d] = (uint64_t*)bind(ho->mult[d], off_mult[d], c->packed[d].rows.size() * 8);
+        dout.endpoint_mult[d] = (uint64_t*)bind(ho->endpoint_mult[d], off_em[d], c->packed[d].erows.size() * 16);
+        if (acc) {
+            if (ho->mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.mult[d], ho->mult[d], c->packed[d].rows.size() * 8, cudaMemcpyHostToDevice, st));
+            if (ho->endpoint_mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.endpoint_mult[d], ho->endpoint_mult[d], c->packed[d].erows.size() * 16, cudaMemcpyHostToDevice, st));
+        }
+    }
+    dout.masked_chars = (uint8_t*)bind(ho->masked_chars, off_mc, n * rp);
+    dout.masked_substr_ids = (uint8_t*)bind(ho->masked_substr_ids, off_ms, n * rp);
+    dout.status = (b2r_string_status*)bind(ho->status, off_st, n * sizeof(b2r_string_status));
+    dout.records = (b2r_substr_record*)bind(ho->records, off_rec, n * (size_t)ho->max_records * sizeof(b2r_substr_record));
+    dout.compact_bytes = (uint8_t*)bind(ho->compact_bytes, off_cb, n * (size_t)ho->compact_pitch);
+
+    // inputs: keep the caller's offsets (the kernel adds them to the base pointer, so shift the base instead)
+    if (nbytes) CUDA_TRY(cudaMemcpyAsync((unsigned char*)c->ws_bytes.p + (base & 15), h_bytes + base, nbytes, cudaMemcpyHostToDevice, st));
+    if (n) CUDA_TRY(cudaMemcpyAsync(c->ws_offsets.p, h_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    // d_bytes + offsets[j] must address string j: d_bytes = ws + (base & 15) - base  (16-byte aligned by construction)
+    const uint8_t* d_bytes = (const uint8_t*)c->ws_bytes.p + (base & 15) - base;
+    rc = match_batch_impl(c, d_bytes, (const uint64_t*)c->ws_offsets.p, n, total, &dout, c->max_chars, st);
+    if (rc) return rc;
+    for (const Copy& cp : copies)
+        if (cp.bytes) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
+    b2r_batch_status r;
+    rc = b2r_batch_result(c, st, &r);
+    if (result) *result = r;
+    return rc;
+}
+
+int b2r_match_substrs(b2r_config* c, const uint8_t* characters, uint64_t len, const b2r_outputs* h_out, b2r_batch_status* result) {
+    if (!c || !h_out) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    const uint64_t offsets[2] = {0, len};
+    return b2r_match_batch_host(c, characters, offsets, 1, h_out, result);
+}
+
+int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2r_outputs* d_out, void* cuda_stream) {
+    (void)c; (void)d_bytes; (void)len; (void)d_out; (void)cuda_stream;
+    set_error("b2r_match_long: the chunked parallel-prefix path is not built yet");
+    return B2R_ERR_UNSUPPORTED;
+}
+
+uint32_t b2r_last_launch_count(const b2r_config* c) { return c ? c->last_launches : 0; }
+int b2r_config_set_timing(b2r_config* c, int enable) { if (!c) return B2R_ERR_INVALID_ARG; c->timing = enable != 0; return B2R_OK; }
+int b2r_last_kernel_ms(b2r_config* c, float* walk_ms, float* total_ms) {
+    if (!c || !c->timing || c->device < 0) { set_error("timing is not enabled on this handle"); return B2R_ERR_INVALID_ARG; }
+    DeviceGuard g(c->device);
+    CUDA_TRY(cudaEventSynchronize(c->ev[2]));
+    if (walk_ms) CUDA_TRY(cudaEventElapsedTime(walk_ms, c->ev[0], c->ev[1]));
+    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[2]));
+    return B2R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle on identical inputs —
+bit-exact for every witness column, status record, substring record and multiplicity counter."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import DEF_SETS, oracle_config, product_config
+from test_oracle_golden import SNIPPETS, _random_strings, expected_masked
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(strings, lead=0):
+    data = np.frombuffer(b"\x00" * lead + b"".join(strings), dtype=np.uint8)
+    offs = np.zeros(len(strings) + 1, dtype=np.uint64)
+    offs[0] = lead
+    offs[1:] = lead + np.cumsum([len(s) for s in strings])
+    return data, offs
+
+
+def _both(set_name, M, strings, lead=0, check=True, **kw):
+    import halo2_regex_b200 as H
+    cfg = product_config(set_name, M)
+    ocfg = oracle_config(set_name, M)
+    data, offs = _pack(strings, lead)
+    kw.setdefault("max_records", 8)
+    kw.setdefault("compact_pitch", 64)
+    g, gres = cfg.match_batch_host(data, offs, check=False, fill=0xCD, **kw)
+    o, ores = ocfg.match_batch(data, offs, **kw)
+    assert gres.code == ores.code
+    if ores.code != 0:
+        assert (gres.string_idx, gres.pos, gres.state, gres.byte, gres.defidx) == (ores.string_idx, ores.pos, ores.state, ores.byte, ores.defidx)
+    assert gres.n_overlap_lo == ores.n_overlap_lo
+    errs = H.compare_outputs(g, o)
+    assert errs == [], "\n".join(errs)
+    return cfg, g, o
+
+
+def test_golden_vectors_on_gpu(golden_vectors):
+    """G1-G9 straight through the product API (the reference tests' own expectations)."""
+    import halo2_regex_b200 as H
+    for v in golden_vectors:
+        cfg = product_config(v["defs"], v["M"])
+        r = cfg.match_substrs(v["input"].encode())
+        assert all(r.accepted) == v["verify_ok"], v["name"]
+        if v["substrs"] is not None:
+            mc, ms = expected_masked(v)
+            assert np.array_equal(r.masked_characters, mc), v["name"]       # src/lib.rs:1052-1059
+            assert np.array_equal(r.all_substr_ids, ms), v["name"]
+            assert r.substr_bytes == "".join(s for _, s in v["substrs"]).encode()
+        assert len(r.all_enable_flags) == v["M"] and int(r.all_enable_flags.sum()) == len(v["input"])
+        _both(v["defs"], v["M"], [v["input"].encode()])
+
+
+def test_derive_helpers_match_reference_shapes():
+    cfg = product_config("example", 128)
+    s = b"email was meant for @vitalik."
+    st = cfg.derive_states(s)
+    assert len(st) == 1 and len(st[0]) == len(s) + 1 and st[0][0] == 0 and st[0][-1] == 2
+    ids = cfg.derive_substr_ids(s)
+    assert ids[0] == [0] * 21 + [1] * 7 + [0]
+    is_starts, is_ends = cfg.derive_is_start_end(s)
+    assert len(is_starts[0]) == len(s) + 1 and len(is_ends[0]) == len(s) + 1
+    assert [i for i, x in enumerate(is_starts[0]) if x] == [21]
+    assert is_ends[0][0] is False
+
+
+@pytest.mark.parametrize("set_name", ["regex1", "regex2", "regex3", "test1", "regex3_k3", "three"])
+def test_random_ragged_batches(set_name):
+    rng = random.Random(zlib.crc32(set_name.encode()) + 1)
+    strings = _random_strings(rng, 700, 200, SNIPPETS) + [b"", b"", b"x"]
+    _both(set_name, 201, strings)
+
+
+@pytest.mark.parametrize("lead", [0, 1, 7, 16, 33])
+def test_unaligned_offsets(lead):
+    rng = random.Random(lead)
+    strings = _random_strings(rng, 100, 130, SNIPPETS)
+    _both("test1", 131, strings, lead=lead)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 65, 1000])
+def test_batch_sizes(n):
+    rng = random.Random(n)
+    _both("regex1", 100, _random_strings(rng, n, 99, SNIPPETS))
+
+
+def test_empty_batch_and_empty_strings():
+    _both("regex1", 64, [])
+    _both("regex1", 64, [b""] * 40)
+    _both("regex3", 1, [b""] * 3)          # M = 1: only the final-state row exists
+
+
+@pytest.mark.parametrize("M", [16, 17, 63, 64, 65, 128, 129, 1024, 1025])
+def test_max_length_strings(M):
+    """len = M-1 is the longest legal string: the final state lands in the last row (src/lib.rs:404-418)."""
+    rng = random.Random(M)
+    strings = [bytes(rng.choice(b"abc @.\r\n") for _ in range(M - 1)) for _ in range(5)]
+    strings += [b"email was meant for @ab." + b"z" * (M - 25) if M >= 25 else b"q" * (M - 1)]
+    _both("test1", M, strings)
+
+
+def test_config1_shape_fixed_length():
+    """BASELINE config 1 at reduced N: 1 KiB strings, M = 1025, regex1+substr1."""
+    from halo2_regex_b200 import workloads as W
+    data, _ = W.config1_numpy(2048, 1024)
+    strings = [bytes(r) for r in data]
+    cfg, g, o = _both("regex1", 1025, strings, compact_pitch=8)
+    acc = (g.status["flags"] & 1).astype(bool)
+    assert 0.9 < acc.mean() < 0.97          # 15 in 16 strings carry a match
+    assert int(g.mult[0].sum()) == 2048 * 1025
+
+
+def test_config1_ragged():
+    from halo2_regex_b200 import workloads as W
+    data, _ = W.config1_numpy(1024, 1024)
+    flat, offs = W.ragged_from_fixed(data, 99)
+    strings = [bytes(flat[int(offs[i]):int(offs[i + 1])]) for i in range(1024)]
+    _both("regex1", 1025, strings)
+
+
+def test_invalid_transition_reports_reference_panic():
+    import halo2_regex_b200 as H
+    good = b"email was meant for @vitalik."
+    strings = [good, good[:10] + b"X" + good[11:], good, b"\xff"]
+    cfg, g, o = _both("example", 64, strings)
+    assert g.status["flags"][1] & H._abi.B2R_ST_INVALID_TRANSITION
+    with pytest.raises(H.InvalidTransitionError, match=r"The transition from \d+ by 88 is invalid!"):
+        cfg.match_strings(strings)
+    # lowest def wins even when a later def fails earlier in the string (derive_states walks def 0 first)
+    spec = [("regex1_test_lookup.txt", ["substr1_test_lookup.txt"]), ("ex_allstr.txt", ["ex_substr_id1.txt"])]
+    _both(spec, 64, [b"zz\x01", b"email was \x01", b"email was meant for @vitalik."])
+    spec.reverse()
+    _both(spec, 64, [b"zz\x01", b"email was \x01", b"email was meant for @vitalik."])
+
+
+def test_too_long_string():
+    import halo2_regex_b200 as H
+    cfg, g, o = _both("regex1", 16, [b"a" * 15, b"a" * 16, b"b" * 3])
+    assert g.status["flags"][1] & H._abi.B2R_ST_TOO_LONG
+    with pytest.raises(H.StringTooLongError):
+        cfg.match_strings([b"a" * 16])
+
+
+def test_long_substrings_and_multi_run_segments():
+    """Dense substring coverage (long masked stretches, vector fill path) and hand-made defs whose id sum changes
+    inside a masked segment without a flag (the re-walk path)."""
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    allstr = b"0\n3\n3\n" + b"".join(f"{s} {t} {c}\n".encode() for s, t, c in [
+        (0, 0, 120), (0, 1, 97), (1, 1, 97), (1, 2, 98), (2, 2, 98), (2, 3, 99), (3, 3, 120), (3, 1, 97), (2, 1, 97), (1, 3, 99)])
+    # substr A covers a-runs, substr B covers b-runs; start only at 0->1 / 3->1, end only at ->3: A,B alternate unflagged
+    sub_a = b"9\n0\n9\n0 3\n3\n0 1\n1 1\n3 1\n1 3\n2 1\n"
+    sub_b = b"9\n0\n9\n\n3\n1 2\n2 2\n2 3\n"
+    rng = random.Random(5)
+    strings = [bytes(rng.choice(b"xaabbc") for _ in range(rng.randrange(0, 300))) for _ in range(300)]
+    strings += [b"x" + b"a" * 250 + b"c", b"a" * 100 + b"b" * 100 + b"c" + b"x" * 20, b"aabbaabbc", b"aabb"]
+    M = 301
+    pa = H.AllstrRegexDef.read_from_reader(allstr)
+    cfg = H.RegexVerifyConfig.configure(M, [H.RegexDefs(pa, [H.SubstrRegexDef.read_from_reader(sub_a), H.SubstrRegexDef.read_from_reader(sub_b)])])
+    ocfg = O.OracleConfig([(O.OracleAllstr(allstr), [O.OracleSubstr(sub_a), O.OracleSubstr(sub_b)])], M)
+    data, offs = _pack(strings)
+    g, gres = cfg.match_batch_host(data, offs, max_records=16, compact_pitch=512, fill=0xCD)
+    o, ores = ocfg.match_batch(data, offs, max_records=16, compact_pitch=512)
+    assert H.compare_outputs(g, o) == []
+    assert (g.status["n_records"] > 1).any() and (g.status["n_compact"] > 200).any()
+
+
+def test_overlapping_defs_are_flagged():
+    """Two defs flagging the same row: out of the reference's boolean domain (SURVEY 8(a) out-of-domain ii)."""
+    import halo2_regex_b200 as H
+    spec = [("regex1_test_lookup.txt", ["substr1_test_lookup.txt"]), ("regex1_test_lookup.txt", ["substr1_test_lookup.txt"])]
+    cfg, g, o = _both(spec, 64, [b"email was meant for @ab.", b"nothing here", b" email was meant for @q. "])
+    assert g.status["flags"][0] & H._abi.B2R_ST_OVERLAP and not g.status["flags"][1] & H._abi.B2R_ST_OVERLAP
+
+
+def test_null_columns_and_truncation():
+    rng = random.Random(21)
+    strings = _random_strings(rng, 200, 150, SNIPPETS)
+    for want in ({"status", "masked_chars"}, {"states", "status", "mult"}, {"status", "records", "compact_bytes", "masked_substr_ids"},
+                 {"start_enable", "end_enable", "status", "endpoint_mult"}):
+        _both("test1", 151, strings, want=want)
+    _both("regex3", 151, strings, max_records=1, compact_pitch=3)      # truncation flags and exact counts
+
+
+def test_accumulate_multiplicities():
+    import halo2_regex_b200 as H
+    rng = random.Random(8)
+    a, b = _random_strings(rng, 150, 90, SNIPPETS), _random_strings(rng, 170, 90, SNIPPETS)
+    cfg, ocfg = product_config("test1", 91), oracle_config("test1", 91)
+    g, _ = cfg.match_strings(a)
+    g, _ = cfg.match_strings(b, out=cfg.new_host_outputs(len(b)), flags=0)
+    da, oa = _pack(a)
+    db, ob = _pack(b)
+    out = cfg.new_host_outputs(len(b))
+    first, _ = cfg.match_batch_host(da, oa)
+    for d in range(2):
+        out.mult[d][:] = first.mult[d]
+        out.endpoint_mult[d][:] = first.endpoint_mult[d]
+    cfg.match_batch_host(db, ob, out=out, flags=H._abi.B2R_OUT_ACCUMULATE_MULT)
+    o, _ = ocfg.match_strings(a + b)
+    for d in range(2):
+        assert np.array_equal(out.mult[d], o.mult[d])
+        assert np.array_equal(out.endpoint_mult[d], o.endpoint_mult[d])
+        assert int(out.mult[d].sum()) == (len(a) + len(b)) * 91
+
+
+def test_device_pointer_entry_point():
+    """b2r_match_batch with device tensors on a non-default stream; outputs copied back and compared."""
+    import torch
+    import halo2_regex_b200 as H
+    rng = random.Random(77)
+    strings = _random_strings(rng, 3000, 120, SNIPPETS)
+    cfg, ocfg = product_config("three", 121), oracle_config("three", 121)
+    data, offs = _pack(strings)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        d_bytes = torch.from_numpy(data.copy()).cuda()
+        d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+        out = H.DeviceOutputs(cfg, len(strings), max_records=8, compact_pitch=64)
+        cfg.match_batch_device(d_bytes, d_offs, out, stream=stream)
+        res = cfg.batch_result(stream=stream)
+    assert res.code == 0 and cfg.last_launch_count() == 2
+    o, _ = ocfg.match_batch(data, offs, max_records=8, compact_pitch=64)
+    assert H.compare_outputs(out.to_host(), o) == []
+
+
+def test_wide_state_column():
+    """> 255 states: the state column becomes u16 (SURVEY 8(d) w_s = 2)."""
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    S = 300
+    lines = [f"0\n{S - 1}\n{S - 1}\n"]
+    for s in range(S):
+        for c in (97, 98, 99):
+            nxt = (s + 1) % S if c == 97 else (s * 7 + 3) % S if c == 98 else s
+            lines.append(f"{s} {nxt} {c}\n")
+    allstr = "".join(lines).encode()
+    sub = b"5\n0\n9\n10 20\n11 21 30\n10 11\n20 21\n11 12\n21 22\n12 13\n29 30\n28 29\n"
+    rng = random.Random(4)
+    strings = [bytes(rng.choice(b"aaaabc") for _ in range(rng.randrange(0, 400))) for _ in range(200)] + [b"a" * 399]
+    M = 400
+    cfg = H.RegexVerifyConfig.configure(M, [H.RegexDefs(H.AllstrRegexDef.read_from_reader(allstr), [H.SubstrRegexDef.read_from_reader(sub)])])
+    assert cfg.state_widths == [2]
+    ocfg = O.OracleConfig([(O.OracleAllstr(allstr), [O.OracleSubstr(sub)])], M)
+    data, offs = _pack(strings)
+    g, _ = cfg.match_batch_host(data, offs, fill=0xCD)
+    o, _ = ocfg.match_batch(data, offs)
+    assert H.compare_outputs(g, o) == []
+    assert int(g.states[0].max()) > 255
+
+
+def test_multiplicity_invariant_full_size_property():
+    """Size-independent property at a larger N (oracle too slow to be the checker): sum(mult) = N*M, row 0 = padded
+    rows, accepted fraction as planted, masked bytes equal the planted names."""
+    import torch
+    import halo2_regex_b200 as H
+    from halo2_regex_b200 import workloads as W
+    N, L, M = 1 << 15, 1024, 1025
+    cfg = product_config("regex1", M)
+    d_bytes = W.config1_torch(N, L, device="cuda").reshape(-1)
+    d_offs = torch.arange(N + 1, dtype=torch.int64, device="cuda") * L
+    out = H.DeviceOutputs(cfg, N, compact_pitch=8, max_records=2)
+    cfg.match_batch_device(d_bytes, d_offs, out)
+    assert cfg.batch_result().code == 0
+    mult = out.mult[0].cpu().numpy().astype(np.uint64)
+    assert int(mult.sum()) == N * M and int(mult[0]) == N * (M - L)
+    h_data, plan = W.config1_numpy(N, L)
+    status = out.status.cpu().numpy().view(H._abi.STATUS_DTYPE).reshape(-1)
+    acc = (status["flags"] & 1).astype(bool)
+    assert np.array_equal(acc | ~plan["has_match"], np.ones(N, bool))
+    mc = out.masked_chars.cpu().numpy()
+    j = int(np.nonzero(plan["has_match"])[0][5])
+    o, nl = int(plan["offset"][j]) + 21, int(plan["name_len"][j])
+    assert bytes(mc[j, o:o + nl]) == bytes(h_data[j, o:o + nl])
