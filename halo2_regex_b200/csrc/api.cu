@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -61,6 +62,9 @@ struct b2r_config {
     void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
     size_t scratch_bytes = 0;
     b2r_batch_status* d_batch_status = nullptr;
+    uint32_t* direct_tab = nullptr;   // device copy of the direct [256][64] tables (null: class-compressed kernel)
+    uint32_t direct_hist_off = 0;
+    int force_generic = 0;            // testing hook: B2R_FORCE_GENERIC=1 keeps the class-compressed kernel
     WalkParams last = {};
     bool have_last = false;
     uint32_t last_launches = 0;
@@ -124,6 +128,14 @@ int upload_tables(b2r_config* c) {
         c->dev[d].ep_end = (unsigned long long*)(sb + so); so += ep;
     }
     CUDA_TRY(cudaMalloc((void**)&c->d_batch_status, sizeof(b2r_batch_status)));
+    if (direct_table_applicable(c->packed, c->n_defs)) {
+        std::vector<uint32_t> tab;
+        build_direct_table(c->packed, c->n_defs, tab, c->direct_hist_off);
+        CUDA_TRY(cudaMalloc((void**)&c->direct_tab, tab.size() * 4));
+        CUDA_TRY(cudaMemcpy(c->direct_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    }
+    const char* fg = getenv("B2R_FORCE_GENERIC");
+    c->force_generic = fg && fg[0] == '1';
     return B2R_OK;
 }
 
@@ -162,6 +174,10 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     for (uint32_t d = 0; d < c->n_defs; d++) p.want_hist |= (o->mult[d] != nullptr);
+    uint64_t ep = 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;
+    ep = (ep + 15) & ~15ull;
+    p.ep_smem_bytes = ep <= 8192 ? (uint32_t)ep : 0u;   // many substrs x many states: count with global atomics instead
 }
 
 int enqueue_finalize(b2r_config* c, const b2r_outputs* o, uint64_t n, uint64_t max_chars, cudaStream_t st) {
@@ -318,7 +334,7 @@ void b2r_config_free(b2r_config* c) {
     if (!c) return;
     if (c->device >= 0) {
         DeviceGuard g(c->device);
-        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
+        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status); cudaFree(c->direct_tab);
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -372,7 +388,8 @@ static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_
         for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
         for (uint32_t d = 0; d < c->n_defs; d++)
             if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
-        rc = launch_walk(p, wide, st, nullptr);
+        const bool direct = c->direct_tab && !c->force_generic && (p.bitmap_pitch % 16 == 0);
+        rc = direct ? launch_walk_direct(p, c->direct_tab, c->direct_hist_off, st, nullptr) : launch_walk(p, wide, st, nullptr);
         if (rc) return rc;
         c->last_launches++;
     }

@@ -69,6 +69,12 @@ struct PackedDef {
     std::vector<uint32_t> erow_start_bin, erow_end_bin;
 };
 
+// Direct [256][64] table of the walk_direct kernel for n_defs defs with <= 64 states each (walk_direct.cuh):
+// entry(c,s) = next<<2 | next<<8 | substr_id<<16 | flags<<24 at u32 index d*16640 + c*65 + s (row stride 65 words); unused slots are 0.
+// hist_off = 128 when every def has <= 32 states (bins share the table rows), else n_defs*66560.
+bool direct_table_applicable(const PackedDef* defs, uint32_t n_defs);
+void build_direct_table(const PackedDef* defs, uint32_t n_defs, std::vector<uint32_t>& out, uint32_t& hist_off);
+
 // returns 0, B2R_ERR_UNSUPPORTED or B2R_ERR_INVALID_ARG (message via set_error)
 int pack_def(const AllstrDef& a, const std::vector<const SubstrDef*>& substrs, uint32_t substr_id_offset, PackedDef& out);
 

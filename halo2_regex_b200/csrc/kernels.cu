@@ -6,6 +6,7 @@
 #include <cstdio>
 
 #include "walk.cuh"
+#include "walk_direct.cuh"
 
 namespace b2r {
 
@@ -55,6 +56,7 @@ int walk_smem_bytes(const WalkParams& p, bool wide, int warps, bool smem_tables,
         if (smem_hist) n += (size_t)256 * p.def[d].num_states * 4;
     }
     n = (n + 15) & ~size_t(15);
+    n += sizeof(CtaCounters) + ((p.ep_smem_bytes + 15u) & ~15u);
     n += (size_t)warps * (wide ? per_warp_smem<uint16_t>(p.n_defs) : per_warp_smem<uint8_t>(p.n_defs));
     return (int)n;
 }
@@ -94,6 +96,36 @@ int launch_walk(const WalkParams& p, bool wide, void* stream, WalkLaunch* chosen
         case 4: return launch_walk_d<4>(p, wide, ts, hs, smem, grid, st);
     }
     set_error("unsupported number of defs %u", p.n_defs);
+    return B2R_ERR_UNSUPPORTED;
+}
+
+template <int D>
+int launch_direct_d(const WalkParams& p, const uint32_t* tab, bool in_row, size_t smem, int grid, int block, cudaStream_t st);
+template <> int launch_direct_d<1>(const WalkParams&, const uint32_t*, bool, size_t, int, int, cudaStream_t);
+template <> int launch_direct_d<2>(const WalkParams&, const uint32_t*, bool, size_t, int, int, cudaStream_t);
+
+int launch_walk_direct(const WalkParams& p, const uint32_t* d_direct_tab, uint32_t hist_off, void* stream, WalkLaunch* chosen) {
+    int dev = 0, n_sm = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const uint32_t D = p.n_defs;
+    const bool in_row = hist_off == 128u;
+    const bool bins = p.want_hist && !in_row;
+    const size_t fixed = (size_t)D * DTAB_BYTES + (bins ? (size_t)D * DTAB_BYTES : 0) + ZERO_BYTES + sizeof(CtaCounters) + p.ep_smem_bytes;
+    const size_t per_warp = (size_t)32 * DPITCH * (1 + D);
+    int warps = (int)(((size_t)max_smem - fixed) / per_warp);
+    if (warps > DIRECT_MAX_THREADS / 32) warps = DIRECT_MAX_THREADS / 32;
+    if (warps < 1) { set_error("direct tables do not fit in shared memory"); return B2R_ERR_UNSUPPORTED; }
+    // persistent: one CTA per SM, tiles strided over (CTA, warp); small batches use fewer CTAs
+    long long ctas = ((long long)p.n_tiles + warps - 1) / warps;
+    int grid = (int)(ctas < n_sm ? (ctas > 0 ? ctas : 1) : n_sm);
+    const size_t smem = fixed + per_warp * warps;
+    if (chosen) { chosen->grid = grid; chosen->block = warps * 32; chosen->smem_bytes = smem; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 1) return launch_direct_d<1>(p, d_direct_tab, in_row, smem, grid, warps * 32, st);
+    if (D == 2) return launch_direct_d<2>(p, d_direct_tab, in_row, smem, grid, warps * 32, st);
+    set_error("direct kernel supports at most 2 defs");
     return B2R_ERR_UNSUPPORTED;
 }
 

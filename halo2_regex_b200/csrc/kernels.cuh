@@ -52,6 +52,7 @@ struct WalkParams {
     uint32_t smem_tables;            // 1: class/transition tables staged in shared memory
     uint32_t smem_hist;              // 1: multiplicity bins accumulated in shared memory, flushed with global atomics
     uint32_t want_hist;              // 0: no multiplicity output was requested, skip the histogram
+    uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
 };
 
 struct FinalizeParams {
@@ -80,6 +81,7 @@ struct WalkLaunch {
 int launch_walk(const WalkParams& p, bool wide_states, void* stream, WalkLaunch* chosen);
 int launch_finalize(const FinalizeParams& p, void* stream);
 int launch_diagnose(const WalkParams& p, uint64_t string_idx, b2r_batch_status* d_out, void* stream);
+int launch_walk_direct(const WalkParams& p, const uint32_t* d_direct_tab, uint32_t hist_off, void* stream, WalkLaunch* chosen);
 int walk_smem_bytes(const WalkParams& p, bool wide_states, int warps, bool smem_tables, bool smem_hist);
 
 }  // namespace b2r

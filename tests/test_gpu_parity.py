@@ -150,7 +150,8 @@ def test_long_substrings_and_multi_run_segments():
     import halo2_regex_b200 as H
     from oracle import oracle as O
     allstr = b"0\n3\n3\n" + b"".join(f"{s} {t} {c}\n".encode() for s, t, c in [
-        (0, 0, 120), (0, 1, 97), (1, 1, 97), (1, 2, 98), (2, 2, 98), (2, 3, 99), (3, 3, 120), (3, 1, 97), (2, 1, 97), (1, 3, 99)])
+        (0, 0, 120), (0, 1, 97), (1, 1, 97), (1, 2, 98), (2, 2, 98), (2, 3, 99), (3, 3, 120), (3, 1, 97), (2, 1, 97), (1, 3, 99),
+        (0, 0, 98), (0, 0, 99), (1, 0, 120), (2, 0, 120), (3, 3, 98), (3, 3, 99)])
     # substr A covers a-runs, substr B covers b-runs; start only at 0->1 / 3->1, end only at ->3: A,B alternate unflagged
     sub_a = b"9\n0\n9\n0 3\n3\n0 1\n1 1\n3 1\n1 3\n2 1\n"
     sub_b = b"9\n0\n9\n\n3\n1 2\n2 2\n2 3\n"
