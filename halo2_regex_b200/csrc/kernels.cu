@@ -113,7 +113,7 @@ int launch_walk_direct(const WalkParams& p, const uint32_t* d_direct_tab, uint32
     const bool in_row = hist_off == 128u;
     const bool bins = p.want_hist && !in_row;
     const size_t fixed = (size_t)D * DTAB_BYTES + (bins ? (size_t)D * DTAB_BYTES : 0) + ZERO_BYTES + sizeof(CtaCounters) + p.ep_smem_bytes;
-    const size_t per_warp = (size_t)32 * DPITCH * (1 + D);
+    const size_t per_warp = (size_t)direct_tile_bytes_per_warp((int)D);
     int warps = (int)(((size_t)max_smem - fixed) / per_warp);
     if (warps > DIRECT_MAX_THREADS / 32) warps = DIRECT_MAX_THREADS / 32;
     if (warps < 1) { set_error("direct tables do not fit in shared memory"); return B2R_ERR_UNSUPPORTED; }

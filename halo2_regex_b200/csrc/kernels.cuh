@@ -30,6 +30,8 @@ struct BatchCounters {               // zeroed (first_bad = ~0) before every bat
     unsigned long long n_overlap;
     unsigned long long pad_rows;     // sum over strings of (M - len): multiplicity of table row 0
     unsigned long long n_ok_strings; // strings that were walked to the end
+    unsigned long long tile_counter; // next tile of 32 strings to hand out (dynamic scheduling of the persistent CTAs)
+    unsigned long long reserved[3];
 };
 
 struct WalkParams {

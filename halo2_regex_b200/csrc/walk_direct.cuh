@@ -1,25 +1,27 @@
 // walk_direct_kernel — the hot kernel for definitions with at most 64 states per def (all shipped DFAs: 13..29 states).
 //
-// One LANE per string, one WARP per tile of 32 strings, persistent CTAs (one per SM).
+// One LANE per string, one WARP per tile of 32 strings, persistent CTAs (one per SM), tiles handed out by an atomic counter.
 //
 // Shared memory per CTA
-//   table  D x 64 KiB   direct next-state table: entry (u32) of (byte c, state s) at c*260 + s*4 (row stride 65 words: bank = (c+s) mod 32), so that ONE byte-permute
-//                       builds the address from the previous entry (byte0 = s<<2) and the input word (byte1 = c):
-//                         entry = [ next<<2 | next<<8 | substr_id<<16 | flags<<24 ]   (flags: is_start, is_end, invalid)
-//                       this is the "dense 256 x S next-state table staged into shared memory" of the north star, padded to 64
-//                       states per byte;
-//   hist   D x 64 KiB   multiplicity bins, same (c,s) addressing (+HIST_OFF); when S <= 32 the bins live in the unused upper
-//                       half of each 256-byte table row instead (HIST_OFF = 128) and no extra memory is needed;
-//   zero   2 KiB        source of the TMA bulk zero-fills;
-//   per warp            input tile 32 x (CH+16) B and state tile D x 32 x (CH+16) B.
+//   table  D x 65 KiB   direct next-state table: entry (u32) of (byte c, state s) at c*260 + s*4.  The 65-word row stride
+//                       makes the bank (c + s) mod 32, so lanes sitting in the same state with different bytes do not
+//                       conflict.  entry = [ next<<2 | next<<8 | substr_id<<16 | flags<<24 ] (flags: is_start, is_end,
+//                       invalid): ONE byte-permute of the previous entry (byte0 = s<<2) and the input word (byte1 = c)
+//                       gives c*256 + s*4, and c*4 + table base is added off the dependent chain.  This is the "dense
+//                       256 x S next-state table staged into shared memory" of the north star, padded to 65 slots per byte;
+//   hist               multiplicity bins with the same (c,s) addressing: inside the unused upper half of each table row when
+//                       S <= 32 (HIST_IN_ROW, +128 B), else a second D x 65 KiB region;
+//   zero   8 KiB        source of the TMA bulk zero-fills;
+//   per warp            2 input tiles (double buffer) of 32 x (DCH+16) B and a state tile of D x 32 x (DCH+16) B.
 //
 // Per tile
-//   1. every lane zero-fills ITS rows of the sparse columns (substr ids, enable bitmaps, masked chars / ids) with TMA bulk
-//      stores (cp.async.bulk shared->global) from the zero buffer — no LSU instructions, completion awaited lazily;
-//   2. chunks of CH positions: the warp stages the 32 strings' bytes with coalesced 16-byte loads into the padded tile,
-//      each lane walks its own string with conflict-free LDS.128 reads:  PRMT (address) -> LDS (entry) per byte on the
-//      dependent chain, plus one ATOMS.POPC.INC (multiplicity bin), one PRMT (state byte into the output pack) and one
-//      LOP3+branch (rare-row test) off the chain; states go back through the state tile and out with coalesced 16-byte stores;
+//   1. lane 0 zero-fills the tile's 32 adjacent rows of every sparse column (substr ids, enable bitmaps, masked chars / ids)
+//      with TMA bulk stores (cp.async.bulk shared->global) from the zero buffer, one tile AHEAD of the walk;
+//   2. chunks of DCH positions: cp.async (16 B, zero-filled past the string end) stages chunk k+1 of the 32 strings into
+//      the spare input tile while chunk k is walked; each lane reads ITS string with conflict-free LDS.128 and walks it:
+//      PRMT (address) -> IADD -> LDS (entry) per byte on the dependent chain, plus one shared-memory atomic (multiplicity
+//      bin), PRMT (state byte into the output pack) and the rare-row test off the chain; states go back through the state
+//      tile and out with coalesced 16-byte stores;
 //   3. rare rows are queued and replayed at the end of the string (rare.cuh), in lockstep across the warp.
 #pragma once
 #include "rare.cuh"
@@ -28,13 +30,14 @@ namespace b2r {
 
 constexpr int DCH = 64;               // positions per staged chunk
 constexpr int DPITCH = DCH + 16;      // tile row pitch: 5 x 16 B keeps per-lane LDS.128 / STS.128 conflict-free
-constexpr int ZERO_BYTES = 2048;
+constexpr int ZERO_BYTES = 8192;
 constexpr uint32_t DROW = 260;                 // bytes per table row (byte value): 65 words, so bank = (c + s) mod 32
 constexpr uint32_t DTAB_BYTES = 256 * DROW;    // 66,560 B per def
 constexpr int DIRECT_MAX_STATES = 64;
 constexpr int DIRECT_MAX_THREADS = 512;
+__host__ __device__ constexpr int direct_tile_bytes_per_warp(int D) { return 32 * DPITCH * (2 + D); }
 
-// direct-table entry encoding (built by build_direct_table in kernels.cu)
+// direct-table entry encoding (built by build_direct_table in defs.cpp)
 constexpr uint32_t DE_RARE_MASK = 0xFFFF0000u;   // substr id + flags
 constexpr uint32_t DE_SID_MASK = 0x00FF0000u;
 
@@ -45,37 +48,45 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte async copy global -> shared; copies src_bytes (0 or 16) and zero-fills the rest
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int D, bool HIST, bool HIST_IN_ROW>
 __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(const __grid_constant__ WalkParams p, const uint32_t* __restrict__ gtab) {
     constexpr uint32_t hist_off = HIST_IN_ROW ? 128u : D * DTAB_BYTES;
-    constexpr bool want_hist = HIST;
     extern __shared__ __align__(1024) unsigned char dsmem[];
     unsigned char* const smem = dsmem;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int n_warps = blockDim.x >> 5;
 
     // ---- shared memory carve-up --------------------------------------------------------------------------------
-    unsigned char* const tab = smem;                                   // D x 64 KiB (+ D x 64 KiB bins when hist_off = D*64 KiB)
+    unsigned char* const tab = smem;                                   // D tables (+ D bin regions unless HIST_IN_ROW)
     const uint32_t tab_bytes = D * DTAB_BYTES;
-    const uint32_t bins_bytes = HIST_IN_ROW ? 0u : tab_bytes;
+    const uint32_t bins_bytes = (HIST && !HIST_IN_ROW) ? tab_bytes : 0u;
     unsigned char* const zero = smem + tab_bytes + bins_bytes;
     CtaCounters* const cc = reinterpret_cast<CtaCounters*>(zero + ZERO_BYTES);
     unsigned char* const ep_base = zero + ZERO_BYTES + sizeof(CtaCounters);
     uint32_t* ep_s[D];
     ep_smem_layout<D>(p, ep_base, ep_s);
     unsigned char* const tiles = ep_base + p.ep_smem_bytes;
-    unsigned char* const in_tile = tiles + (size_t)warp * (32 * DPITCH * (1 + D));
-    unsigned char* const st_tile = in_tile + 32 * DPITCH;
+    unsigned char* const in_tile0 = tiles + (size_t)warp * direct_tile_bytes_per_warp(D);
+    unsigned char* const st_tile = in_tile0 + 2 * 32 * DPITCH;
     {
         const uint4* g = reinterpret_cast<const uint4*>(gtab);
         uint4* s4 = reinterpret_cast<uint4*>(tab);
@@ -91,8 +102,47 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
     const uint32_t Mpad = (M + 15u) & ~15u;                             // rows written (row_pitch >= Mpad by contract)
     const uint32_t n_chunks = (Mpad + DCH - 1) / DCH;
     const uint64_t rp = p.row_pitch;
+    const uint32_t tab_s = smem_u32(tab);
+    const uint32_t zero_s = smem_u32(zero);
+    const uint32_t in_s = smem_u32(in_tile0);
+    const int kv = lane & 3, r0 = lane >> 2;                            // staging: this lane moves vector kv of rows r0 + 8*i
 
-    for (uint32_t tile = blockIdx.x * n_warps + warp; tile < p.n_tiles; tile += gridDim.x * n_warps) {
+    // lane 0: TMA zero-fill of the 32 adjacent rows of tile t in every sparse column
+    auto zero_fill_tile = [&](uint32_t t) {
+        const uint64_t base = (uint64_t)t * 32;
+        const uint64_t rows = (p.n_strings - base < 32) ? (p.n_strings - base) : 32;
+        auto fill = [&](uint8_t* ptr, uint64_t bytes) {
+            for (uint64_t o = 0; o < bytes; o += ZERO_BYTES) bulk_store(ptr + o, zero_s, (uint32_t)(bytes - o < ZERO_BYTES ? bytes - o : ZERO_BYTES));
+        };
+        if (p.masked_chars) fill(p.masked_chars + base * rp, rows * rp);
+        if (p.masked_substr_ids) fill(p.masked_substr_ids + base * rp, rows * rp);
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (p.def[d].substr_ids) fill(p.def[d].substr_ids + base * rp, rows * rp);
+            if (p.def[d].start_enable) fill(p.def[d].start_enable + base * p.bitmap_pitch, rows * p.bitmap_pitch);
+            if (p.def[d].end_enable) fill(p.def[d].end_enable + base * p.bitmap_pitch, rows * p.bitmap_pitch);
+        }
+        bulk_commit();
+    };
+    auto next_tile = [&]() -> uint32_t {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&p.counters->tile_counter, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        return t < p.n_tiles ? (uint32_t)t : 0xFFFFFFFFu;
+    };
+
+    uint32_t tile = next_tile();
+    if (tile != 0xFFFFFFFFu && lane == 0) zero_fill_tile(tile);
+
+    while (tile != 0xFFFFFFFFu) {
+        const uint32_t tile_after = next_tile();
+        // the zero-fill of THIS tile was issued one tile ago: wait for it, then start the next one
+        if (lane == 0) {
+            bulk_wait_all();
+            if (tile_after != 0xFFFFFFFFu) zero_fill_tile(tile_after);
+        }
+        __syncwarp();
+
         const uint64_t tile_base = (uint64_t)tile * 32;
         const uint64_t idx = tile_base + lane;
         const bool valid = idx < p.n_strings;
@@ -115,30 +165,11 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
             k.tb[d].tab = tab + d * DTAB_BYTES; k.ep_s[d] = ep_s[d];
         }
 
-        // (1) TMA zero-fill of this lane's rows of the sparse columns
-        if (valid) {
-            auto zero_row = [&](uint8_t* row, uint32_t bytes) {
-                for (uint32_t o = 0; o < bytes; o += ZERO_BYTES) bulk_store(row + o, zero, min(bytes - o, (uint32_t)ZERO_BYTES));
-            };
-            if (p.masked_chars) zero_row(p.masked_chars + idx * rp, Mpad);
-            if (p.masked_substr_ids) zero_row(p.masked_substr_ids + idx * rp, Mpad);
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                if (p.def[d].substr_ids) zero_row(p.def[d].substr_ids + idx * rp, Mpad);
-                if (p.def[d].start_enable) zero_row(p.def[d].start_enable + idx * p.bitmap_pitch, (uint32_t)p.bitmap_pitch);
-                if (p.def[d].end_enable) zero_row(p.def[d].end_enable + idx * p.bitmap_pitch, (uint32_t)p.bitmap_pitch);
-            }
-            bulk_commit();
-        }
-        bool zero_done = false;
-
-        // staging geometry: this lane moves vector kv of rows r0 + 8*i (i = 0..3)
+        // staging geometry
         const uint32_t shift = (uint32_t)(off & 15);
         const bool any_shift = __any_sync(0xffffffffu, shift != 0);
-        const int kv = lane & 3, r0 = lane >> 2;
-        const uint8_t* in_ptr[4];
-        uint32_t in_left[4];                                            // bytes of the row from vector kv of chunk 0 to the string end
-        uint64_t st_off[4];
+        const uint8_t* in_ptr[4];                                       // vector kv of chunk 0 of row r0 + 8*i
+        uint32_t in_left[4];                                            // bytes from there to the end of that string
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int row = r0 + 8 * i;
@@ -147,78 +178,77 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
             const uint64_t a = (roff & ~uint64_t(15)) + (uint32_t)kv * 16;
             in_ptr[i] = p.bytes + a;
             in_left[i] = rend > a ? (uint32_t)(rend - a) : 0u;
-            st_off[i] = (tile_base + row) * rp + (uint32_t)kv * 16;
         }
+        const uint64_t tail_a = (off & ~uint64_t(15)) + 64;             // fifth vector of this lane's own row (unaligned strings)
+        const uint8_t* const my_tail = p.bytes + tail_a;
+        const uint32_t my_tail_left = end > tail_a ? (uint32_t)(end - tail_a) : 0u;
         const uint32_t rows_here = (p.n_strings - tile_base < 32) ? (uint32_t)(p.n_strings - tile_base) : 32u;
+
+        auto stage = [&](uint32_t chunk) {   // async copy of chunk `chunk` into input tile (chunk & 1)
+            const uint32_t cbase = chunk * DCH;
+            const uint32_t dst = in_s + (chunk & 1) * (32 * DPITCH) + kv * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) cp_async16(dst + (r0 + 8 * i) * DPITCH, in_ptr[i] + cbase, cbase < in_left[i] ? 16u : 0u);
+            if (any_shift) cp_async16(in_s + (chunk & 1) * (32 * DPITCH) + lane * DPITCH + 64, my_tail + cbase, cbase < my_tail_left ? 16u : 0u);
+            cp_async_commit();
+        };
+        stage(0);
 
 #pragma unroll 1
         for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
             const uint32_t cbase = chunk * DCH;
-            // (2a) stage the input chunk (coalesced 16-byte loads -> padded tile)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (cbase < in_left[i]) val = *reinterpret_cast<const uint4*>(in_ptr[i] + cbase);
-                *reinterpret_cast<uint4*>(in_tile + (r0 + 8 * i) * DPITCH + kv * 16) = val;
-            }
-            if (any_shift) {   // unaligned strings need a fifth vector per row
-                const uint64_t a = (off & ~uint64_t(15)) + cbase + 64;
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (a < end) val = *reinterpret_cast<const uint4*>(p.bytes + a);
-                *reinterpret_cast<uint4*>(in_tile + lane * DPITCH + 64) = val;
-            }
+            if (chunk + 1 < n_chunks) { stage(chunk + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
             __syncwarp();
 
-            // (2b) walk this lane's string over [cbase, cbase + DCH)
-            const unsigned char* my_in = in_tile + lane * DPITCH;
+            // walk this lane's string over [cbase, cbase + DCH)
+            const uint32_t my_in = in_s + (chunk & 1) * (32 * DPITCH) + lane * DPITCH;
 #pragma unroll 1
             for (int g = 0; g < DCH / 16; g++) {
                 const uint32_t gbase = cbase + g * 16;
                 if (gbase >= Mpad) break;
                 uint32_t w[4];
                 if (!any_shift) {
-                    const uint4 t = *reinterpret_cast<const uint4*>(my_in + g * 16);
-                    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my_in + g * 16));
                 } else {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(my_in + g * 16 + (shift & ~3u));
+                    const uint32_t q = my_in + g * 16 + (shift & ~3u);
                     const uint32_t sh = (shift & 3u) * 8;
-                    const uint32_t x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], x4 = q[4];
+                    const uint32_t x0 = lds32(q), x1 = lds32(q + 4), x2 = lds32(q + 8), x3 = lds32(q + 12), x4 = lds32(q + 16);
                     w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh);
                     w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
                 }
                 uint32_t pk[D][4];
                 if (gbase + 16 <= L && !dead) {
-                    // ---- hot path: 16 real characters --------------------------------------------------------------
+                    // ---- hot path: 16 real characters (structured control flow only: the warp reconverges after every rare row)
 #pragma unroll
                     for (int b = 0; b < 16; b++) {
                         uint32_t nxt[D];
                         uint32_t rare = 0;
 #pragma unroll
                         for (int d = 0; d < D; d++) {
-                            // address = state<<2 (byte 0 of cur) | c<<8 (byte b of the input word); upper bytes = sign(flags byte) = 0
-                            const uint32_t c = prmt(w[b >> 2], 0u, 0x4440u + (b & 3));              // off the chain
-                            const uint32_t addr = prmt(cur[d], w[b >> 2], 0xBB40u + ((b & 3) << 4)) + (c << 2);   // c*260 + s*4
-                            nxt[d] = *reinterpret_cast<const uint32_t*>(tab + d * DTAB_BYTES + addr);
-                            if (want_hist) atomicAdd(reinterpret_cast<uint32_t*>(tab + d * DTAB_BYTES + hist_off + addr), 1u);
-                            // state byte (byte 1 of cur) into byte (b&3) of the output pack
+                            const uint32_t c = prmt(w[b >> 2], 0u, 0x4440u + (b & 3));
+                            const uint32_t cb = tab_s + d * DTAB_BYTES + (c << 2);                       // off the chain
+                            const uint32_t addr = prmt(cur[d], w[b >> 2], 0xBB40u + ((b & 3) << 4)) + cb;   // base + c*260 + s*4
+                            nxt[d] = lds32(addr);
+                            if (HIST) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + hist_off) : "memory");
                             const uint32_t sel = (b & 3) == 0 ? 0x3215u : (b & 3) == 1 ? 0x3250u : (b & 3) == 2 ? 0x3510u : 0x5210u;
-                            pk[d][b >> 2] = prmt(pk[d][b >> 2], cur[d], sel);
+                            pk[d][b >> 2] = prmt(pk[d][b >> 2], cur[d], sel);                           // state byte into the output pack
                             rare |= (nxt[d] ^ expect[d]) & DE_RARE_MASK;
                         }
                         if (rare) {
                             uint32_t inval = 0;
-                            Event<D>& ev = k.q[k.nq];
-                            ev.pos = gbase + b; ev.c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
 #pragma unroll
-                            for (int d = 0; d < D; d++) {
-                                ev.e[d] = nxt[d]; ev.s[d] = (cur[d] >> 8) & 0xFFu; ev.nx[d] = (nxt[d] >> 8) & 0xFFu;
-                                expect[d] = nxt[d] & DE_SID_MASK;
-                                inval |= nxt[d] & ENT_INVALID;
-                            }
-                            if (inval) { dead = true; kill_string<D, DirectTables>(p, k); break; }
-                            if (++k.nq == QCAP) {
-                                if (!zero_done) { bulk_wait_all(); zero_done = true; }
-                                drain<D, DirectTables>(p, k);
+                            for (int d = 0; d < D; d++) inval |= nxt[d] & ENT_INVALID;
+                            if (inval) {
+                                if (!dead) { dead = true; kill_string<D, DirectTables>(p, k); }
+                            } else if (!dead) {
+                                Event<D>& ev = k.q[k.nq];
+                                ev.pos = gbase + b; ev.c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+#pragma unroll
+                                for (int d = 0; d < D; d++) {
+                                    ev.e[d] = nxt[d]; ev.s[d] = (cur[d] >> 8) & 0xFFu; ev.nx[d] = (nxt[d] >> 8) & 0xFFu;
+                                    expect[d] = nxt[d] & DE_SID_MASK;
+                                }
+                                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
                             }
                         }
 #pragma unroll
@@ -228,37 +258,35 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                     // ---- ragged end: characters, then the final-state row, then dummy rows -------------------------
 #pragma unroll
                     for (int d = 0; d < D; d++) pk[d][0] = pk[d][1] = pk[d][2] = pk[d][3] = 0;
+                    uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];   // shifted along: no dynamic register indexing
 #pragma unroll 1
                     for (int b = 0; b < 16; b++) {
                         const uint32_t pos = gbase + b;
-                        const uint32_t c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+                        const uint32_t c = v0 & 0xFFu;
+                        v0 = __funnelshift_r(v0, v1, 8); v1 = __funnelshift_r(v1, v2, 8); v2 = __funnelshift_r(v2, v3, 8); v3 >>= 8;
                         uint32_t stb[D];
                         if (pos < L && !dead) {
                             uint32_t nxt[D];
-                            uint32_t rare = 0;
+                            uint32_t rare = 0, inval = 0;
 #pragma unroll
                             for (int d = 0; d < D; d++) {
-                                const uint32_t addr = (cur[d] & 0xFFu) + c * DROW;
-                                nxt[d] = *reinterpret_cast<const uint32_t*>(tab + d * DTAB_BYTES + addr);
-                                if (want_hist) atomicAdd(reinterpret_cast<uint32_t*>(tab + d * DTAB_BYTES + hist_off + addr), 1u);
+                                const uint32_t addr = tab_s + d * DTAB_BYTES + (cur[d] & 0xFFu) + c * DROW;
+                                nxt[d] = lds32(addr);
+                                if (HIST) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + hist_off) : "memory");
                                 stb[d] = (cur[d] >> 8) & 0xFFu;
                                 rare |= (nxt[d] ^ expect[d]) & DE_RARE_MASK;
+                                inval |= nxt[d] & ENT_INVALID;
                             }
-                            if (rare) {
-                                uint32_t inval = 0;
+                            if (inval) { dead = true; kill_string<D, DirectTables>(p, k); }
+                            else if (rare) {
                                 Event<D>& ev = k.q[k.nq];
                                 ev.pos = pos; ev.c = c;
 #pragma unroll
                                 for (int d = 0; d < D; d++) {
                                     ev.e[d] = nxt[d]; ev.s[d] = stb[d]; ev.nx[d] = (nxt[d] >> 8) & 0xFFu;
                                     expect[d] = nxt[d] & DE_SID_MASK;
-                                    inval |= nxt[d] & ENT_INVALID;
                                 }
-                                if (inval) { dead = true; kill_string<D, DirectTables>(p, k); }
-                                else if (++k.nq == QCAP) {
-                                    if (!zero_done) { bulk_wait_all(); zero_done = true; }
-                                    drain<D, DirectTables>(p, k);
-                                }
+                                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
                             }
                             if (!dead) {
 #pragma unroll
@@ -271,7 +299,6 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                                 uint32_t fs[D];
 #pragma unroll
                                 for (int d = 0; d < D; d++) fs[d] = (cur[d] >> 8) & 0xFFu;
-                                if (!zero_done) { bulk_wait_all(); zero_done = true; }
                                 finish_string<D, DirectTables>(p, k, fs);
                             }
                         }
@@ -288,31 +315,32 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
             }
             __syncwarp();
 
-            // (2c) store the state tile (coalesced 16-byte vectors)
+            // store the state tile (coalesced 16-byte vectors)
+            if (cbase + kv * 16 < Mpad) {
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                if (!p.def[d].states) continue;
-                uint8_t* base = reinterpret_cast<uint8_t*>(p.def[d].states) + cbase;
+                for (int d = 0; d < D; d++) {
+                    if (!p.def[d].states) continue;
+                    uint8_t* base = reinterpret_cast<uint8_t*>(p.def[d].states) + (tile_base + r0) * rp + cbase + kv * 16;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int row = r0 + 8 * i;
-                    if (row < (int)rows_here && cbase + kv * 16 < Mpad)
-                        *reinterpret_cast<uint4*>(base + st_off[i]) = *reinterpret_cast<const uint4*>(st_tile + (d * 32 + row) * DPITCH + kv * 16);
+                    for (int i = 0; i < 4; i++) {
+                        if (r0 + 8 * i < (int)rows_here)
+                            *reinterpret_cast<uint4*>(base + (uint64_t)(8 * i) * rp) = *reinterpret_cast<const uint4*>(st_tile + (d * 32 + r0 + 8 * i) * DPITCH + kv * 16);
+                    }
                 }
             }
             __syncwarp();
         }
-        if (!zero_done && valid) bulk_wait_all();
 
         // per-tile counters: rows with enable = 0 all look up table row 0 (src/lib.rs:218-232 with enable = 0)
         cta_counters_tile(cc, valid && !dead, M - L, (k.flags & B2R_ST_OVERLAP) != 0);
+        tile = tile_after;
     }
 
     __syncthreads();
     cta_counters_flush<D>(p, ep_s, cc);
 
     // ---- flush the multiplicity bins: bin (c,s) of def d -> dense global histogram [c*S + s] -----------------------------
-    if (want_hist) {
+    if (HIST) {
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t S = p.def[d].num_states;
