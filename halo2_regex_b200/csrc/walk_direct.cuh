@@ -67,6 +67,59 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ uint32_t lds8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// Exact, in-order replay of the rare rows of one chunk, run once per chunk by the whole warp in lockstep.
+// The hot path only sets bit n of `bits` when word n (rows cbase+4n .. cbase+4n+3) contains an entry whose substr id /
+// flags differ from `expect` AS IT WAS AT THE START OF THE CHUNK (stale).  Here every flagged word is re-examined row by row
+// from shared memory (byte from the input tile, state from the state tile, entry from the table); while the true `expect`
+// differs from the stale one the following words are examined too, flagged or not, so no id change is missed.
+// n_words: words of the chunk the hot path has walked (later rows belong to the ragged path, which is exact by itself).
+// in_s / st_s: shared addresses of this lane's input bytes (shift applied) and state bytes of def 0 for row cbase.
+template <int D>
+__device__ __noinline__ uint32_t chunk_rare(const WalkParams& p, Cold<D, DirectTables>& k, uint32_t bits, uint32_t n_words, uint32_t cbase, uint32_t in_s,
+                                            uint32_t st_s, uint32_t tab_s, uint32_t* expect) {
+    uint32_t stale[D];
+    bool differs = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) stale[d] = expect[d];
+    uint32_t n = bits ? (uint32_t)__ffs((int)bits) - 1u : 16u;
+    while (n < n_words) {   // n_words = words of this chunk walked by the hot path so far
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            const uint32_t r = n * 4 + j;
+            const uint32_t c = lds8(in_s + r);
+            uint32_t e[D], sv[D];
+            uint32_t rare = 0, inval = 0;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                sv[d] = lds8(st_s + d * (32 * DPITCH) + r);
+                e[d] = lds32(tab_s + d * DTAB_BYTES + c * DROW + sv[d] * 4);
+                rare |= (e[d] ^ expect[d]) & DE_RARE_MASK;
+                inval |= e[d] & ENT_INVALID;
+            }
+            if (inval) { kill_string<D, DirectTables>(p, k); return 1; }   // the reference panics here (src/lib.rs:817)
+            if (rare) {
+                Event<D>& ev = k.q[k.nq];
+                ev.pos = cbase + r; ev.c = c;
+#pragma unroll
+                for (int d = 0; d < D; d++) { ev.e[d] = e[d]; ev.s[d] = sv[d]; ev.nx[d] = (e[d] >> 8) & 0xFFu; expect[d] = e[d] & DE_SID_MASK; }
+                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
+            }
+        }
+        bits &= ~(1u << n);
+        differs = false;
+#pragma unroll
+        for (int d = 0; d < D; d++) differs = differs || expect[d] != stale[d];
+        n = differs ? n + 1 : (bits ? (uint32_t)__ffs((int)bits) - 1u : 16u);
+    }
+    return 0;
+}
+
 template <int D, bool HIST, bool HIST_IN_ROW>
 __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(const __grid_constant__ WalkParams p, const uint32_t* __restrict__ gtab) {
     constexpr uint32_t hist_off = HIST_IN_ROW ? 128u : D * DTAB_BYTES;
@@ -202,6 +255,18 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
 
             // walk this lane's string over [cbase, cbase + DCH)
             const uint32_t my_in = in_s + (chunk & 1) * (32 * DPITCH) + lane * DPITCH;
+            const uint32_t my_st = smem_u32(st_tile) + lane * DPITCH;
+            uint32_t rare_bits = 0;                                     // words of this chunk with a rare row (hot path only)
+            uint32_t hot_words = 0;                                     // words of this chunk walked by the hot path
+            auto replay = [&]() {   // out-of-line exact replay; only copies escape, cur/expect stay in registers
+                uint32_t tx[D];
+#pragma unroll
+                for (int d = 0; d < D; d++) tx[d] = expect[d];
+                if (!dead) dead = chunk_rare<D>(p, k, rare_bits, hot_words, cbase, my_in + shift, my_st, tab_s, tx) != 0;
+#pragma unroll
+                for (int d = 0; d < D; d++) expect[d] = tx[d];
+                rare_bits = 0;
+            };
 #pragma unroll 1
             for (int g = 0; g < DCH / 16; g++) {
                 const uint32_t gbase = cbase + g * 16;
@@ -218,44 +283,33 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                 }
                 uint32_t pk[D][4];
                 if (gbase + 16 <= L && !dead) {
-                    // ---- hot path: 16 real characters (structured control flow only: the warp reconverges after every rare row)
+                    // ---- hot path: 16 real characters.  Per byte: PRMT+IMAD (byte*4 + table base, off the chain), PRMT -> IADD -> LDS
+                    // (the chain), one shared atomic (multiplicity bin), PRMT (state byte into the pack), LOP3 (rare accumulate);
+                    // the rare test runs once per 4 bytes and only records a bit.
 #pragma unroll
-                    for (int b = 0; b < 16; b++) {
-                        uint32_t nxt[D];
-                        uint32_t rare = 0;
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t acc = 0;
 #pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            const uint32_t c = prmt(w[b >> 2], 0u, 0x4440u + (b & 3));
-                            const uint32_t cb = tab_s + d * DTAB_BYTES + (c << 2);                       // off the chain
-                            const uint32_t addr = prmt(cur[d], w[b >> 2], 0xBB40u + ((b & 3) << 4)) + cb;   // base + c*260 + s*4
-                            nxt[d] = lds32(addr);
-                            if (HIST) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + hist_off) : "memory");
-                            const uint32_t sel = (b & 3) == 0 ? 0x3215u : (b & 3) == 1 ? 0x3250u : (b & 3) == 2 ? 0x3510u : 0x5210u;
-                            pk[d][b >> 2] = prmt(pk[d][b >> 2], cur[d], sel);                           // state byte into the output pack
-                            rare |= (nxt[d] ^ expect[d]) & DE_RARE_MASK;
-                        }
-                        if (rare) {
-                            uint32_t inval = 0;
+                        for (int j = 0; j < 4; j++) {
 #pragma unroll
-                            for (int d = 0; d < D; d++) inval |= nxt[d] & ENT_INVALID;
-                            if (inval) {
-                                if (!dead) { dead = true; kill_string<D, DirectTables>(p, k); }
-                            } else if (!dead) {
-                                Event<D>& ev = k.q[k.nq];
-                                ev.pos = gbase + b; ev.c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
-#pragma unroll
-                                for (int d = 0; d < D; d++) {
-                                    ev.e[d] = nxt[d]; ev.s[d] = (cur[d] >> 8) & 0xFFu; ev.nx[d] = (nxt[d] >> 8) & 0xFFu;
-                                    expect[d] = nxt[d] & DE_SID_MASK;
-                                }
-                                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
+                            for (int d = 0; d < D; d++) {
+                                const uint32_t c = prmt(w[q], 0u, 0x4440u + j);
+                                const uint32_t cb = tab_s + d * DTAB_BYTES + (c << 2);                   // off the chain
+                                const uint32_t addr = prmt(cur[d], w[q], 0xBB40u + (j << 4)) + cb;       // base + c*260 + s*4
+                                const uint32_t e = lds32(addr);
+                                if (HIST) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + hist_off) : "memory");
+                                const uint32_t sel = j == 0 ? 0x3215u : j == 1 ? 0x3250u : j == 2 ? 0x3510u : 0x5210u;
+                                pk[d][q] = prmt(pk[d][q], cur[d], sel);                                 // state byte into the output pack
+                                acc |= e ^ expect[d];
+                                cur[d] = e;
                             }
                         }
-#pragma unroll
-                        for (int d = 0; d < D; d++) cur[d] = nxt[d];
+                        if (acc & DE_RARE_MASK) rare_bits |= 1u << (g * 4 + q);   // replayed once per chunk (chunk_rare)
                     }
+                    hot_words = g * 4 + 4;
                 } else {
                     // ---- ragged end: characters, then the final-state row, then dummy rows -------------------------
+                    if (rare_bits) replay();   // keep the queued rows in position order
 #pragma unroll
                     for (int d = 0; d < D; d++) pk[d][0] = pk[d][1] = pk[d][2] = pk[d][3] = 0;
                     uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];   // shifted along: no dynamic register indexing
@@ -314,6 +368,7 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                     *reinterpret_cast<uint4*>(st_tile + (d * 32 + lane) * DPITCH + g * 16) = make_uint4(pk[d][0], pk[d][1], pk[d][2], pk[d][3]);
             }
             __syncwarp();
+            if (__any_sync(0xffffffffu, rare_bits != 0)) replay();   // lockstep: costs the longest lane, not the sum over lanes
 
             // store the state tile (coalesced 16-byte vectors)
             if (cbase + kv * 16 < Mpad) {
