@@ -62,6 +62,7 @@ struct b2r_config {
     void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
     size_t scratch_bytes = 0;
     b2r_batch_status* d_batch_status = nullptr;
+    uint32_t* queue = nullptr;        // per-lane rare-row queues (global scratch, L2-resident)
     uint32_t* direct_tab = nullptr;   // device copy of the direct [256][64] tables (null: class-compressed kernel)
     uint32_t direct_hist_off = 0;
     int force_generic = 0;            // testing hook: B2R_FORCE_GENERIC=1 keeps the class-compressed kernel
@@ -134,6 +135,12 @@ int upload_tables(b2r_config* c) {
         CUDA_TRY(cudaMalloc((void**)&c->direct_tab, tab.size() * 4));
         CUDA_TRY(cudaMemcpy(c->direct_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
+    {   // rare-row queues: one slice per resident lane of the largest launch (8 CTAs x 256 threads or 1 x 512 per SM)
+        int n_sm = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+        const size_t lanes = (size_t)n_sm * 2048;
+        CUDA_TRY(cudaMalloc((void**)&c->queue, lanes * (size_t)(8 * (1 + 2 * c->n_defs)) * 4));
+    }
     const char* fg = getenv("B2R_FORCE_GENERIC");
     c->force_generic = fg && fg[0] == '1';
     return B2R_OK;
@@ -172,6 +179,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.status = o->status; p.records = o->records; p.compact_bytes = o->compact_bytes;
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
     p.counters = (BatchCounters*)c->scratch;
+    p.queue = c->queue;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     for (uint32_t d = 0; d < c->n_defs; d++) p.want_hist |= (o->mult[d] != nullptr);
     uint64_t ep = 0;
@@ -334,7 +342,7 @@ void b2r_config_free(b2r_config* c) {
     if (!c) return;
     if (c->device >= 0) {
         DeviceGuard g(c->device);
-        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status); cudaFree(c->direct_tab);
+        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status); cudaFree(c->direct_tab); cudaFree(c->queue);
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);

@@ -54,6 +54,7 @@ struct WalkParams {
     uint32_t smem_tables;            // 1: class/transition tables staged in shared memory
     uint32_t smem_hist;              // 1: multiplicity bins accumulated in shared memory, flushed with global atomics
     uint32_t want_hist;              // 0: no multiplicity output was requested, skip the histogram
+    uint32_t* queue;                 // global scratch for the per-lane rare-row queues: grid*block lanes x queue_words(D) words
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
 };
 

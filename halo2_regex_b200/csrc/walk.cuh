@@ -29,6 +29,19 @@ struct StTile {
     static constexpr int VPR = ROW_BYTES / 16;          // vectors per row
 };
 
+// one rare row handled immediately, out of line (class-compressed entry encoding: next state in bits 0..15)
+template <int D>
+__device__ __noinline__ void rare_row_generic(const WalkParams& p, const Cold<D, 1>& k, const RowCtx<D, ClassTables>& x, uint32_t pos, const uint32_t* e,
+                                              const uint32_t* s, uint32_t* expect) {
+    uint32_t nx[D], run_sid[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) { nx[d] = e[d] & ENT_NEXT_MASK; run_sid[d] = expect[d] >> 16; }
+    (void)nx; (void)run_sid;
+    push_row<D, 1, ClassTables>(p, k, x, pos, e, s);
+#pragma unroll
+    for (int d = 0; d < D; d++) expect[d] = e[d] & ENT_SID_MASK;
+}
+
 template <int D, typename ST, bool TBL_SMEM, bool HIST_SMEM, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -87,20 +100,23 @@ __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant_
         const bool valid = idx < p.n_strings;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[idx]; end = p.offsets[idx + 1]; }
-        Cold<D, ClassTables> k;
+        uint32_t cold_store[cold_fields(D)];                              // cold state in local memory (stride 1)
+        const Cold<D, 1> k{cold_store};
         bool dead = !valid;
         if (valid && (end < off || end - off > (uint64_t)(M - 1))) {     // len must be <= M-1
             dead = true; end = off;
-            k.idx = idx;
-            kill_string<D, ClassTables>(p, k);
+            kill_string(p, idx);
         }
         const uint32_t L = (uint32_t)(end - off);
-        k.init(idx, p.bytes + off, L);
+        k.init();
+        RowCtx<D, ClassTables> x;
+        x.idx = idx; x.src = p.bytes + off; x.len = L; x.tile_pos = NO_POS; x.tile_s = 0;
+        x.qbase = p.queue + ((size_t)(blockIdx.x * WARPS + warp) * queue_words(D)) * 32 + lane;
         uint32_t s[D], expect[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
             s[d] = p.def[d].first_state; expect[d] = 0;
-            k.tb[d].cls = cls_t[d]; k.tb[d].trans = trans_t[d]; k.tb[d].S = S_[d]; k.ep_s[d] = ep_s[d];
+            x.tb[d].cls = cls_t[d]; x.tb[d].trans = trans_t[d]; x.tb[d].S = S_[d]; x.ep_s[d] = ep_s[d];
         }
         const uint64_t abase = off & ~uint64_t(15);
         const uint32_t shift = (uint32_t)(off & 15);
@@ -195,18 +211,19 @@ __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant_
                             pk[d][b] = (ST)s[d];
                             rare |= (e[d] ^ expect[d]) & ENT_RARE_MASK;
                         }
-                        if (rare) {   // queue the row (rare.cuh); only the queue entry escapes, s/e/expect stay in registers
+                        if (rare) {   // only copies escape to the out-of-line call: s/e/expect stay in registers
                             uint32_t inval = 0;
-                            Event<D>& ev = k.q[k.nq];
-                            ev.pos = gbase + b; ev.c = c;
 #pragma unroll
-                            for (int d = 0; d < D; d++) {
-                                ev.e[d] = e[d]; ev.s[d] = s[d]; ev.nx[d] = e[d] & ENT_NEXT_MASK;
-                                expect[d] = e[d] & ENT_SID_MASK;
-                                inval |= e[d] & ENT_INVALID;
+                            for (int d = 0; d < D; d++) inval |= e[d] & ENT_INVALID;
+                            if (inval) { if (!dead) { dead = true; kill_string(p, idx); } }
+                            else if (!dead) {
+                                uint32_t te[D], ts[D], tx[D];
+#pragma unroll
+                                for (int d = 0; d < D; d++) { te[d] = e[d]; ts[d] = s[d]; tx[d] = expect[d]; }
+                                rare_row_generic<D>(p, k, x, gbase + b, te, ts, tx);
+#pragma unroll
+                                for (int d = 0; d < D; d++) expect[d] = tx[d];
                             }
-                            if (inval) { dead = true; kill_string<D, ClassTables>(p, k); break; }
-                            if (++k.nq == QCAP) drain<D, ClassTables>(p, k);
                         }
 #pragma unroll
                         for (int d = 0; d < D; d++) s[d] = e[d] & ENT_NEXT_MASK;
@@ -236,16 +253,17 @@ __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant_
                                 reinterpret_cast<ST*>(st_tile + (d * 32 + lane) * StTile<ST>::PITCH)[g * 16 + b] = (ST)s[d];
                             if (rare) {
                                 uint32_t inval = 0;
-                                Event<D>& ev = k.q[k.nq];
-                                ev.pos = pos; ev.c = c;
 #pragma unroll
-                                for (int d = 0; d < D; d++) {
-                                    ev.e[d] = e[d]; ev.s[d] = s[d]; ev.nx[d] = e[d] & ENT_NEXT_MASK;
-                                    expect[d] = e[d] & ENT_SID_MASK;
-                                    inval |= e[d] & ENT_INVALID;
+                                for (int d = 0; d < D; d++) inval |= e[d] & ENT_INVALID;
+                                if (inval) { dead = true; kill_string(p, idx); }
+                                else {
+                                    uint32_t te[D], ts[D], tx[D];
+#pragma unroll
+                                    for (int d = 0; d < D; d++) { te[d] = e[d]; ts[d] = s[d]; tx[d] = expect[d]; }
+                                    rare_row_generic<D>(p, k, x, pos, te, ts, tx);
+#pragma unroll
+                                    for (int d = 0; d < D; d++) expect[d] = tx[d];
                                 }
-                                if (inval) { dead = true; kill_string<D, ClassTables>(p, k); }
-                                else if (++k.nq == QCAP) drain<D, ClassTables>(p, k);
                             }
                             if (!dead) {
 #pragma unroll
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant_
                                 uint32_t ts[D];
 #pragma unroll
                                 for (int d = 0; d < D; d++) ts[d] = s[d];
-                                finish_string<D, ClassTables>(p, k, ts);
+                                finish_string<D, 1, ClassTables>(p, k, x, ts);
                             }
                         }
                     }
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant_
         }
 
         // per-tile counters: rows with enable = 0 all look up table row 0 (src/lib.rs:218-232 with enable = 0)
-        cta_counters_tile(cc, valid && !dead, M - L, (k.flags & B2R_ST_OVERLAP) != 0);
+        cta_counters_tile(cc, valid && !dead, M - L, (cold_store[CF_FLAGS] & B2R_ST_OVERLAP) != 0);
     }
 
     __syncthreads();

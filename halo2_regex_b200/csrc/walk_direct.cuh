@@ -12,7 +12,8 @@
 //   hist               multiplicity bins with the same (c,s) addressing: inside the unused upper half of each table row when
 //                       S <= 32 (HIST_IN_ROW, +128 B), else a second D x 65 KiB region;
 //   zero   8 KiB        source of the TMA bulk zero-fills;
-//   per warp            2 input tiles (double buffer) of 32 x (DCH+16) B and a state tile of D x 32 x (DCH+16) B.
+//   per warp            2 input tiles (double buffer) of 32 x (DCH+16) B, a state tile of D x 32 x (DCH+16) B and the
+//                       lanes' cold state (struct of arrays).
 //
 // Per tile
 //   1. lane 0 zero-fills the tile's 32 adjacent rows of every sparse column (substr ids, enable bitmaps, masked chars / ids)
@@ -22,7 +23,8 @@
 //      PRMT (address) -> IADD -> LDS (entry) per byte on the dependent chain, plus one shared-memory atomic (multiplicity
 //      bin), PRMT (state byte into the output pack) and the rare-row test off the chain; states go back through the state
 //      tile and out with coalesced 16-byte stores;
-//   3. rare rows are queued and replayed at the end of the string (rare.cuh), in lockstep across the warp.
+//   3. the hot path only flags words that contain a rare row; they are replayed exactly, in order, once per chunk by the
+//      whole warp in lockstep (chunk_rare), with the lane's cold state in shared memory (rare.cuh).
 #pragma once
 #include "rare.cuh"
 
@@ -35,7 +37,7 @@ constexpr uint32_t DROW = 260;                 // bytes per table row (byte valu
 constexpr uint32_t DTAB_BYTES = 256 * DROW;    // 66,560 B per def
 constexpr int DIRECT_MAX_STATES = 64;
 constexpr int DIRECT_MAX_THREADS = 512;
-__host__ __device__ constexpr int direct_tile_bytes_per_warp(int D) { return 32 * DPITCH * (2 + D); }
+__host__ __device__ constexpr int direct_tile_bytes_per_warp(int D) { return 32 * DPITCH * (2 + D) + cold_fields(D) * 128; }
 
 // direct-table entry encoding (built by build_direct_table in defs.cpp)
 constexpr uint32_t DE_RARE_MASK = 0xFFFF0000u;   // substr id + flags
@@ -67,10 +69,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint32_t lds8(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
+// one rare row handled immediately (ragged path), out of line
+template <int D>
+__device__ __noinline__ void rare_row_now(const WalkParams& p, const Cold<D, 32>& k, const RowCtx<D, DirectTables>& x, uint32_t pos, const uint32_t* e,
+                                          const uint32_t* s, uint32_t* expect) {
+    uint32_t nx[D], run_sid[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) { nx[d] = (e[d] >> 8) & 0xFFu; run_sid[d] = expect[d] >> 16; }
+    (void)nx; (void)run_sid;
+    push_row<D, 32, DirectTables>(p, k, x, pos, e, s);
+#pragma unroll
+    for (int d = 0; d < D; d++) expect[d] = e[d] & DE_SID_MASK;
 }
 
 // Exact, in-order replay of the rare rows of one chunk, run once per chunk by the whole warp in lockstep.
@@ -79,16 +88,17 @@ __device__ __forceinline__ uint32_t lds8(uint32_t saddr) {
 // from shared memory (byte from the input tile, state from the state tile, entry from the table); while the true `expect`
 // differs from the stale one the following words are examined too, flagged or not, so no id change is missed.
 // n_words: words of the chunk the hot path has walked (later rows belong to the ragged path, which is exact by itself).
-// in_s / st_s: shared addresses of this lane's input bytes (shift applied) and state bytes of def 0 for row cbase.
+// x.tile_s / st_s: shared addresses of this lane's input bytes (shift applied) and state bytes of def 0 for row cbase.
+// Returns non-zero when the string died (invalid transition: the reference panics, src/lib.rs:817).
 template <int D>
-__device__ __noinline__ uint32_t chunk_rare(const WalkParams& p, Cold<D, DirectTables>& k, uint32_t bits, uint32_t n_words, uint32_t cbase, uint32_t in_s,
+__device__ __noinline__ uint32_t chunk_rare(const WalkParams& p, const Cold<D, 32>& k, const RowCtx<D, DirectTables>& x, uint32_t bits, uint32_t n_words,
                                             uint32_t st_s, uint32_t tab_s, uint32_t* expect) {
-    uint32_t stale[D];
-    bool differs = false;
+    const uint32_t cbase = x.tile_pos, in_s = x.tile_s;
+    uint32_t stale[D], run_sid[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) stale[d] = expect[d];
+    for (int d = 0; d < D; d++) { stale[d] = expect[d]; run_sid[d] = expect[d] >> 16; }
     uint32_t n = bits ? (uint32_t)__ffs((int)bits) - 1u : 16u;
-    while (n < n_words) {   // n_words = words of this chunk walked by the hot path so far
+    while (n < n_words) {
 #pragma unroll 1
         for (int j = 0; j < 4; j++) {
             const uint32_t r = n * 4 + j;
@@ -99,24 +109,24 @@ __device__ __noinline__ uint32_t chunk_rare(const WalkParams& p, Cold<D, DirectT
             for (int d = 0; d < D; d++) {
                 sv[d] = lds8(st_s + d * (32 * DPITCH) + r);
                 e[d] = lds32(tab_s + d * DTAB_BYTES + c * DROW + sv[d] * 4);
-                rare |= (e[d] ^ expect[d]) & DE_RARE_MASK;
+                rare |= (e[d] ^ (run_sid[d] << 16)) & DE_RARE_MASK;
                 inval |= e[d] & ENT_INVALID;
             }
-            if (inval) { kill_string<D, DirectTables>(p, k); return 1; }   // the reference panics here (src/lib.rs:817)
+            if (inval) { kill_string(p, x.idx); return 1; }
             if (rare) {
-                Event<D>& ev = k.q[k.nq];
-                ev.pos = cbase + r; ev.c = c;
+                push_row<D, 32, DirectTables>(p, k, x, cbase + r, e, sv);
 #pragma unroll
-                for (int d = 0; d < D; d++) { ev.e[d] = e[d]; ev.s[d] = sv[d]; ev.nx[d] = (e[d] >> 8) & 0xFFu; expect[d] = e[d] & DE_SID_MASK; }
-                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
+                for (int d = 0; d < D; d++) run_sid[d] = ent_sid(e[d]);
             }
         }
         bits &= ~(1u << n);
-        differs = false;
+        bool differs = false;
 #pragma unroll
-        for (int d = 0; d < D; d++) differs = differs || expect[d] != stale[d];
+        for (int d = 0; d < D; d++) differs = differs || (run_sid[d] << 16) != stale[d];
         n = differs ? n + 1 : (bits ? (uint32_t)__ffs((int)bits) - 1u : 16u);
     }
+#pragma unroll
+    for (int d = 0; d < D; d++) expect[d] = run_sid[d] << 16;
     return 0;
 }
 
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
     unsigned char* const tiles = ep_base + p.ep_smem_bytes;
     unsigned char* const in_tile0 = tiles + (size_t)warp * direct_tile_bytes_per_warp(D);
     unsigned char* const st_tile = in_tile0 + 2 * 32 * DPITCH;
+    const Cold<D, 32> k{reinterpret_cast<uint32_t*>(st_tile + D * 32 * DPITCH) + lane};   // cold state, struct of arrays
     {
         const uint4* g = reinterpret_cast<const uint4*>(gtab);
         uint4* s4 = reinterpret_cast<uint4*>(tab);
@@ -201,22 +212,27 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
         const bool valid = idx < p.n_strings;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[idx]; end = p.offsets[idx + 1]; }
-        Cold<D, DirectTables> k;
         bool dead = !valid;
         if (valid && (end < off || end - off > (uint64_t)(M - 1))) {    // len must be <= M-1
             dead = true; end = off;
-            k.idx = idx;
-            kill_string<D, DirectTables>(p, k);
+            kill_string(p, idx);
         }
         const uint32_t L = (uint32_t)(end - off);
-        k.init(idx, p.bytes + off, L);
+        k.init();
         uint32_t cur[D], expect[D];                                     // cur = entry that led to the current state
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t f = p.def[d].first_state;
             cur[d] = (f << 2) | (f << 8); expect[d] = 0;
-            k.tb[d].tab = tab + d * DTAB_BYTES; k.ep_s[d] = ep_s[d];
         }
+        auto make_ctx = [&](uint32_t tile_pos, uint32_t tile_s) {       // built from registers where the rare path is entered
+            RowCtx<D, DirectTables> x;
+            x.idx = idx; x.src = p.bytes + off; x.len = L; x.tile_pos = tile_pos; x.tile_s = tile_s;
+#pragma unroll
+            for (int d = 0; d < D; d++) { x.tb[d].tab = tab + d * DTAB_BYTES; x.ep_s[d] = ep_s[d]; }
+            x.qbase = p.queue + ((size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * queue_words(D)) * 32 + lane;
+            return x;
+        };
 
         // staging geometry
         const uint32_t shift = (uint32_t)(off & 15);
@@ -262,7 +278,10 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                 uint32_t tx[D];
 #pragma unroll
                 for (int d = 0; d < D; d++) tx[d] = expect[d];
-                if (!dead) dead = chunk_rare<D>(p, k, rare_bits, hot_words, cbase, my_in + shift, my_st, tab_s, tx) != 0;
+                if (!dead) {
+                    const RowCtx<D, DirectTables> x = make_ctx(cbase, my_in + shift);
+                    dead = chunk_rare<D>(p, k, x, rare_bits, hot_words, my_st, tab_s, tx) != 0;
+                }
 #pragma unroll
                 for (int d = 0; d < D; d++) expect[d] = tx[d];
                 rare_bits = 0;
@@ -331,16 +350,15 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
                                 rare |= (nxt[d] ^ expect[d]) & DE_RARE_MASK;
                                 inval |= nxt[d] & ENT_INVALID;
                             }
-                            if (inval) { dead = true; kill_string<D, DirectTables>(p, k); }
+                            if (inval) { dead = true; kill_string(p, idx); }
                             else if (rare) {
-                                Event<D>& ev = k.q[k.nq];
-                                ev.pos = pos; ev.c = c;
+                                const RowCtx<D, DirectTables> x = make_ctx(cbase, my_in + shift);
+                                uint32_t te[D], ts[D], tx[D];
 #pragma unroll
-                                for (int d = 0; d < D; d++) {
-                                    ev.e[d] = nxt[d]; ev.s[d] = stb[d]; ev.nx[d] = (nxt[d] >> 8) & 0xFFu;
-                                    expect[d] = nxt[d] & DE_SID_MASK;
-                                }
-                                if (++k.nq == QCAP) drain<D, DirectTables>(p, k);
+                                for (int d = 0; d < D; d++) { te[d] = nxt[d]; ts[d] = stb[d]; tx[d] = expect[d]; }
+                                rare_row_now<D>(p, k, x, pos, te, ts, tx);
+#pragma unroll
+                                for (int d = 0; d < D; d++) expect[d] = tx[d];
                             }
                             if (!dead) {
 #pragma unroll
@@ -350,10 +368,11 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
 #pragma unroll
                             for (int d = 0; d < D; d++) stb[d] = (pos <= L) ? ((cur[d] >> 8) & 0xFFu) : p.def[d].num_states;   // final state, then dummy
                             if (pos == L && !dead) {
+                                const RowCtx<D, DirectTables> x = make_ctx(cbase, my_in + shift);
                                 uint32_t fs[D];
 #pragma unroll
                                 for (int d = 0; d < D; d++) fs[d] = (cur[d] >> 8) & 0xFFu;
-                                finish_string<D, DirectTables>(p, k, fs);
+                                finish_string<D, 32, DirectTables>(p, k, x, fs);
                             }
                         }
 #pragma unroll
@@ -387,7 +406,7 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
         }
 
         // per-tile counters: rows with enable = 0 all look up table row 0 (src/lib.rs:218-232 with enable = 0)
-        cta_counters_tile(cc, valid && !dead, M - L, (k.flags & B2R_ST_OVERLAP) != 0);
+        cta_counters_tile(cc, valid && !dead, M - L, (k.f(CF_FLAGS) & B2R_ST_OVERLAP) != 0);
         tile = tile_after;
     }
 
