@@ -27,7 +27,7 @@ class HostOutputs:
     """
 
     def __init__(self, n_strings, max_chars_size, state_widths, table_rows, endpoint_rows, row_pitch=None,
-                 bitmap_pitch=None, max_records=8, compact_pitch=64, want=None, fill=None):
+                 bitmap_pitch=None, max_records=8, compact_pitch=64, want=None, fill=None, allocator=None):
         n, m = int(n_strings), int(max_chars_size)
         self.n, self.m = n, m
         self.n_defs = len(state_widths)
@@ -42,7 +42,8 @@ class HostOutputs:
         rp, bp = self.row_pitch, self.bitmap_pitch
 
         def col(nbytes):
-            a = aligned_empty(nbytes)
+            a = allocator(nbytes) if allocator else aligned_empty(nbytes)   # e.g. page-locked memory for fast D2H
+            assert a.ctypes.data % 16 == 0
             if fill is not None:
                 a[:] = fill
             return a
@@ -65,6 +66,11 @@ class HostOutputs:
     @staticmethod
     def _p(a):
         return None if a is None else a.ctypes.data
+
+    def all_arrays(self):
+        cols = self.states + self.substr_ids + self.start_enable + self.end_enable + self.mult + self.endpoint_mult
+        cols += [self.masked_chars, self.masked_substr_ids, self.status, self.records, self.compact_bytes]
+        return [c for c in cols if c is not None]
 
     def struct(self, flags=0):
         o = _abi.Outputs()

@@ -85,49 +85,73 @@ __device__ __noinline__ void rare_row_now(const WalkParams& p, const Cold<D, 32>
 // Exact, in-order replay of the rare rows of one chunk, run once per chunk by the whole warp in lockstep.
 // The hot path only sets bit n of `bits` when word n (rows cbase+4n .. cbase+4n+3) contains an entry whose substr id /
 // flags differ from `expect` AS IT WAS AT THE START OF THE CHUNK (stale).  Here every flagged word is re-examined row by row
-// from shared memory (byte from the input tile, state from the state tile, entry from the table); while the true `expect`
-// differs from the stale one the following words are examined too, flagged or not, so no id change is missed.
+// from shared memory (4 bytes from the input tile, 4 states from the state tile, 4 independent table lookups); while the
+// true `expect` differs from the stale one the following words are examined too, flagged or not, so no id change is
+// missed.  Rare rows are only QUEUED here (fire-and-forget stores into the lane's L2-resident queue slice); their heavy
+// processing happens at the end of the string, in lockstep (rare.cuh).  All arguments are scalars in registers.
 // n_words: words of the chunk the hot path has walked (later rows belong to the ragged path, which is exact by itself).
-// x.tile_s / st_s: shared addresses of this lane's input bytes (shift applied) and state bytes of def 0 for row cbase.
-// Returns non-zero when the string died (invalid transition: the reference panics, src/lib.rs:817).
+// in_s / st_s: shared addresses of this lane's input bytes (shift applied) and state bytes of def 0 for row cbase.
+// Returns 0 = ok, 1 = invalid transition (the reference panics, src/lib.rs:817), 2 = the queue is full: the caller
+// drains it (out of line) and calls again with the returned *bits / *next_word.
 template <int D>
-__device__ __noinline__ uint32_t chunk_rare(const WalkParams& p, const Cold<D, 32>& k, const RowCtx<D, DirectTables>& x, uint32_t bits, uint32_t n_words,
-                                            uint32_t st_s, uint32_t tab_s, uint32_t* expect) {
-    const uint32_t cbase = x.tile_pos, in_s = x.tile_s;
-    uint32_t stale[D], run_sid[D];
+__device__ __noinline__ uint32_t chunk_rare(uint32_t* cold_base, uint32_t* qbase, uint32_t* bits_io, uint32_t* next_word_io, uint32_t n_words, uint32_t cbase,
+                                            uint32_t in_s, uint32_t st_s, uint32_t tab_s, const uint32_t* stale, uint32_t* expect) {
+    const Cold<D, 32> k{cold_base};
+    uint32_t bits = *bits_io;
+    uint32_t run[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) { stale[d] = expect[d]; run_sid[d] = expect[d] >> 16; }
-    uint32_t n = bits ? (uint32_t)__ffs((int)bits) - 1u : 16u;
+    for (int d = 0; d < D; d++) run[d] = expect[d];
+    uint32_t nq = k.f(CF_NQ);
+    uint32_t n = *next_word_io;
+    if (n == 0xFFFFFFFFu) n = bits ? (uint32_t)__ffs((int)bits) - 1u : 16u;
+    uint32_t rc = 0;
     while (n < n_words) {
-#pragma unroll 1
+        if (nq + 4 > QCAP) { rc = 2; break; }                           // room for the 4 rows of a word
+        uint32_t c[4], sv[D], e[4][D];
+#pragma unroll
+        for (int j = 0; j < 4; j++) c[j] = lds8(in_s + n * 4 + j);
+#pragma unroll
+        for (int d = 0; d < D; d++) sv[d] = lds32(st_s + d * (32 * DPITCH) + n * 4);   // 4 state bytes
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int d = 0; d < D; d++) e[j][d] = lds32(tab_s + d * DTAB_BYTES + c[j] * DROW + ((sv[d] >> (8 * j)) & 0xFFu) * 4);
+#pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t r = n * 4 + j;
-            const uint32_t c = lds8(in_s + r);
-            uint32_t e[D], sv[D];
             uint32_t rare = 0, inval = 0;
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                sv[d] = lds8(st_s + d * (32 * DPITCH) + r);
-                e[d] = lds32(tab_s + d * DTAB_BYTES + c * DROW + sv[d] * 4);
-                rare |= (e[d] ^ (run_sid[d] << 16)) & DE_RARE_MASK;
-                inval |= e[d] & ENT_INVALID;
-            }
-            if (inval) { kill_string(p, x.idx); return 1; }
+            for (int d = 0; d < D; d++) { rare |= (e[j][d] ^ run[d]) & DE_RARE_MASK; inval |= e[j][d] & ENT_INVALID; }
+            if (inval) { rc = 1; break; }
             if (rare) {
-                push_row<D, 32, DirectTables>(p, k, x, cbase + r, e, sv);
+                uint32_t* q = qbase + nq * (1 + 2 * D) * 32;
+                __stcg(q, cbase + n * 4 + j);
 #pragma unroll
-                for (int d = 0; d < D; d++) run_sid[d] = ent_sid(e[d]);
+                for (int d = 0; d < D; d++) {
+                    __stcg(q + (1 + 2 * d) * 32, e[j][d]);
+                    __stcg(q + (2 + 2 * d) * 32, (sv[d] >> (8 * j)) & 0xFFu);
+                    run[d] = e[j][d] & DE_SID_MASK;
+                }
+                nq++;
             }
         }
+        if (rc) break;
         bits &= ~(1u << n);
         bool differs = false;
 #pragma unroll
-        for (int d = 0; d < D; d++) differs = differs || (run_sid[d] << 16) != stale[d];
+        for (int d = 0; d < D; d++) differs = differs || run[d] != stale[d];
         n = differs ? n + 1 : (bits ? (uint32_t)__ffs((int)bits) - 1u : 16u);
     }
+    k.f(CF_NQ) = nq;
 #pragma unroll
-    for (int d = 0; d < D; d++) expect[d] = run_sid[d] << 16;
-    return 0;
+    for (int d = 0; d < D; d++) expect[d] = run[d];
+    *bits_io = bits; *next_word_io = n;
+    return rc;
+}
+
+// out-of-line drain of a full queue in the middle of a string (rare: more than QCAP-3 rare rows pending)
+template <int D>
+__device__ __noinline__ void drain_now(const WalkParams& p, const Cold<D, 32>& k, const RowCtx<D, DirectTables>& x) {
+    drain<D, 32, DirectTables>(p, k, x);
 }
 
 template <int D, bool HIST, bool HIST_IN_ROW>
@@ -275,15 +299,22 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS, 1) walk_direct_kernel(cons
             uint32_t rare_bits = 0;                                     // words of this chunk with a rare row (hot path only)
             uint32_t hot_words = 0;                                     // words of this chunk walked by the hot path
             auto replay = [&]() {   // out-of-line exact replay; only copies escape, cur/expect stay in registers
-                uint32_t tx[D];
-#pragma unroll
-                for (int d = 0; d < D; d++) tx[d] = expect[d];
                 if (!dead) {
-                    const RowCtx<D, DirectTables> x = make_ctx(cbase, my_in + shift);
-                    dead = chunk_rare<D>(p, k, x, rare_bits, hot_words, my_st, tab_s, tx) != 0;
-                }
+                    uint32_t tx[D], ts[D];
 #pragma unroll
-                for (int d = 0; d < D; d++) expect[d] = tx[d];
+                    for (int d = 0; d < D; d++) { tx[d] = expect[d]; ts[d] = expect[d]; }
+                    uint32_t tb = rare_bits, tn = 0xFFFFFFFFu;
+                    uint32_t* const qb = p.queue + ((size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * queue_words(D)) * 32 + lane;
+                    for (;;) {
+                        const uint32_t rc = chunk_rare<D>(k.base, qb, &tb, &tn, hot_words, cbase, my_in + shift, my_st, tab_s, ts, tx);
+                        if (rc == 1) { dead = true; kill_string(p, idx); }
+                        if (rc != 2) break;
+                        const RowCtx<D, DirectTables> x = make_ctx(cbase, my_in + shift);
+                        drain_now<D>(p, k, x);
+                    }
+#pragma unroll
+                    for (int d = 0; d < D; d++) expect[d] = tx[d];
+                }
                 rare_bits = 0;
             };
 #pragma unroll 1

@@ -75,8 +75,15 @@ class DeviceOutputs:
         self.substr_ids = [z((n, rp)) if "substr_ids" in want else None for d in range(D)]
         self.start_enable = [z((n, bp)) if "start_enable" in want else None for d in range(D)]
         self.end_enable = [z((n, bp)) if "end_enable" in want else None for d in range(D)]
-        self.mult = [torch.zeros(cfg.table_num_rows[d], dtype=torch.int64, device=dev) if "mult" in want else None for d in range(D)]
-        self.endpoint_mult = [torch.zeros(2 * cfg.endpoint_num_rows[d], dtype=torch.int64, device=dev) if "endpoint_mult" in want else None for d in range(D)]
+        # every multiplicity counter of the batch lives in ONE flat u64 buffer, so that the multi-GPU path all-reduces it with
+        # a single collective and the finalisation kernel writes straight into the collective's buffer
+        sizes = [cfg.table_num_rows[d] if "mult" in want else 0 for d in range(D)] + [2 * cfg.endpoint_num_rows[d] if "endpoint_mult" in want else 0 for d in range(D)]
+        self.mult_all = torch.zeros(max(sum(sizes), 1), dtype=torch.int64, device=dev)
+        views, o = [], 0
+        for sz in sizes:
+            views.append(self.mult_all[o:o + sz] if sz else None)
+            o += sz
+        self.mult, self.endpoint_mult = views[:D], views[D:]
         self.masked_chars = z((n, rp)) if "masked_chars" in want else None
         self.masked_substr_ids = z((n, rp)) if "masked_substr_ids" in want else None
         self.status = z((n, 32)) if "status" in want else None
