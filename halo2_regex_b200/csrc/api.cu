@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -46,6 +47,7 @@ struct DevBuf {
 struct DevDef {
     uint8_t* byte_class = nullptr;
     uint32_t* trans = nullptr;
+    uint32_t* hot = nullptr;     // walk table [C][P] (walk.cuh)
     uint32_t *row_bin = nullptr, *erow_start_bin = nullptr, *erow_end_bin = nullptr;
     unsigned long long *hist = nullptr, *ep_start = nullptr, *ep_end = nullptr;  // inside cfg->scratch
 };
@@ -62,15 +64,15 @@ struct b2r_config {
     void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
     size_t scratch_bytes = 0;
     b2r_batch_status* d_batch_status = nullptr;
-    uint32_t* queue = nullptr;        // per-lane rare-row queues (global scratch, L2-resident)
-    uint32_t* direct_tab = nullptr;   // device copy of the direct [256][64] tables (null: class-compressed kernel)
-    uint32_t direct_hist_off = 0;
-    int force_generic = 0;            // testing hook: B2R_FORCE_GENERIC=1 keeps the class-compressed kernel
+    int force_table_mode = -1;        // testing hooks: B2R_TABLE_MODE=repl|plain|global, B2R_HIST_MODE=smem|global
+    int force_hist_mode = -1;
+    DevBuf ws_fmask;                  // granule flags (walk -> emit)
+    DevBuf ws_states[B2R_MAX_DEFS];   // state column of a def the caller did not ask for (emit reads it)
     WalkParams last = {};
     bool have_last = false;
     uint32_t last_launches = 0;
     bool timing = false;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before walk, after walk, after emit, after finalize
     // staging for the host-pointer entry point
     DevBuf ws_bytes, ws_offsets, ws_cols;
     cudaStream_t host_stream = nullptr;
@@ -95,7 +97,7 @@ int upload_tables(b2r_config* c) {
     for (uint32_t d = 0; d < c->n_defs; d++) {
         const PackedDef& pd = c->packed[d];
         total += align_up(256, 256) + align_up(pd.trans.size() * 4, 256) + align_up(pd.row_bin.size() * 4, 256) +
-                 2 * align_up(pd.erows.size() * 4, 256);
+                 2 * align_up(pd.erows.size() * 4, 256) + align_up((size_t)pd.num_classes * padded_states(pd.num_states) * 4, 256);
     }
     CUDA_TRY(cudaMalloc(&c->tables, total));
     unsigned char* base = (unsigned char*)c->tables;
@@ -111,6 +113,11 @@ int upload_tables(b2r_config* c) {
         const PackedDef& pd = c->packed[d];
         c->dev[d].byte_class = (uint8_t*)put(pd.byte_class.data(), 256);
         c->dev[d].trans = (uint32_t*)put(pd.trans.data(), pd.trans.size() * 4);
+        {
+            std::vector<uint32_t> hot;
+            build_walk_table(pd, hot);
+            c->dev[d].hot = (uint32_t*)put(hot.data(), hot.size() * 4);
+        }
         c->dev[d].row_bin = (uint32_t*)put(pd.row_bin.data(), pd.row_bin.size() * 4);
         c->dev[d].erow_start_bin = (uint32_t*)put(pd.erow_start_bin.data(), pd.erows.size() * 4);
         c->dev[d].erow_end_bin = (uint32_t*)put(pd.erow_end_bin.data(), pd.erows.size() * 4);
@@ -129,20 +136,10 @@ int upload_tables(b2r_config* c) {
         c->dev[d].ep_end = (unsigned long long*)(sb + so); so += ep;
     }
     CUDA_TRY(cudaMalloc((void**)&c->d_batch_status, sizeof(b2r_batch_status)));
-    if (direct_table_applicable(c->packed, c->n_defs)) {
-        std::vector<uint32_t> tab;
-        build_direct_table(c->packed, c->n_defs, tab, c->direct_hist_off);
-        CUDA_TRY(cudaMalloc((void**)&c->direct_tab, tab.size() * 4));
-        CUDA_TRY(cudaMemcpy(c->direct_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-    }
-    {   // rare-row queues: one slice per resident lane of the largest launch (8 CTAs x 256 threads or 1 x 512 per SM)
-        int n_sm = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-        const size_t lanes = (size_t)n_sm * 2048;
-        CUDA_TRY(cudaMalloc((void**)&c->queue, lanes * (size_t)(8 * (1 + 2 * c->n_defs)) * 4));
-    }
-    const char* fg = getenv("B2R_FORCE_GENERIC");
-    c->force_generic = fg && fg[0] == '1';
+    if (const char* tm = getenv("B2R_TABLE_MODE"))
+        c->force_table_mode = !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
+    if (const char* hm = getenv("B2R_HIST_MODE"))
+        c->force_hist_mode = !strcmp(hm, "smem") ? (int)HIST_SMEM : !strcmp(hm, "global") ? (int)HIST_GLOBAL : -1;
     return B2R_OK;
 }
 
@@ -169,7 +166,8 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     for (uint32_t d = 0; d < c->n_defs; d++) {
         const PackedDef& pd = c->packed[d];
         DefDev& dd = p.def[d];
-        dd.byte_class = c->dev[d].byte_class; dd.trans = c->dev[d].trans;
+        dd.byte_class = c->dev[d].byte_class; dd.trans = c->dev[d].trans; dd.hot = c->dev[d].hot;
+        dd.padded_states = padded_states(pd.num_states);
         dd.num_states = pd.num_states; dd.num_classes = pd.num_classes; dd.first_state = pd.first_state;
         dd.accepted_state = pd.accepted_state; dd.sid_offset = pd.substr_id_offset; dd.num_substrs = pd.num_substrs;
         dd.hist = c->dev[d].hist; dd.ep_start = c->dev[d].ep_start; dd.ep_end = c->dev[d].ep_end;
@@ -179,13 +177,15 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.status = o->status; p.records = o->records; p.compact_bytes = o->compact_bytes;
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
     p.counters = (BatchCounters*)c->scratch;
-    p.queue = c->queue;
     p.n_tiles = (uint32_t)((n + 31) / 32);
-    for (uint32_t d = 0; d < c->n_defs; d++) p.want_hist |= (o->mult[d] != nullptr);
+    p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;
     ep = (ep + 15) & ~15ull;
     p.ep_smem_bytes = ep <= 8192 ? (uint32_t)ep : 0u;   // many substrs x many states: count with global atomics instead
+    uint64_t et = 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) et += (uint64_t)c->packed[d].num_classes * c->packed[d].num_states * 4ull + 256ull;
+    p.emit_smem_tables = et + p.ep_smem_bytes <= 40 * 1024 ? 1u : 0u;
 }
 
 int enqueue_finalize(b2r_config* c, const b2r_outputs* o, uint64_t n, uint64_t max_chars, cudaStream_t st) {
@@ -342,7 +342,9 @@ void b2r_config_free(b2r_config* c) {
     if (!c) return;
     if (c->device >= 0) {
         DeviceGuard g(c->device);
-        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status); cudaFree(c->direct_tab); cudaFree(c->queue);
+        cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
+        c->ws_fmask.release();
+        for (auto& b : c->ws_states) b.release();
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -390,21 +392,35 @@ static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_
     WalkParams& p = c->last;
     fill_walk_params(c, p, d_bytes, d_offsets, n, total_bytes, o, max_chars);
     c->have_last = true;
+    bool wide = false;
+    for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
+    for (uint32_t d = 0; d < c->n_defs; d++)
+        if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
+    if (n) {
+        // walk -> emit hand-over: granule flags, and a scratch state column for every def the caller does not want
+        if ((rc = c->ws_fmask.reserve(std::max<size_t>((size_t)p.fm_words * n * 4, 16)))) return rc;
+        p.fmask = (uint32_t*)c->ws_fmask.p;
+        for (uint32_t d = 0; d < c->n_defs; d++) {
+            if (p.def[d].states) continue;
+            if ((rc = c->ws_states[d].reserve((size_t)n * o->row_pitch * (wide ? 2 : 1)))) return rc;
+            p.def[d].states = c->ws_states[d].p;
+        }
+        if ((rc = plan_walk(p, wide, c->force_table_mode, c->force_hist_mode))) return rc;
+    }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
     if (n) {
-        bool wide = false;
-        for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
-        for (uint32_t d = 0; d < c->n_defs; d++)
-            if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
-        const bool direct = c->direct_tab && !c->force_generic && (p.bitmap_pitch % 16 == 0);
-        rc = direct ? launch_walk_direct(p, c->direct_tab, c->direct_hist_off, st, nullptr) : launch_walk(p, wide, st, nullptr);
-        if (rc) return rc;
+        if ((rc = launch_walk(p, wide, st, nullptr))) return rc;
         c->last_launches++;
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
+    if (n) {
+        if ((rc = launch_emit(p, wide, st, nullptr))) return rc;
+        c->last_launches++;
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
     rc = enqueue_finalize(c, o, n, max_chars, st);
     if (rc) return rc;
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], st));
     return B2R_OK;
 }
 
@@ -534,9 +550,22 @@ int b2r_config_set_timing(b2r_config* c, int enable) { if (!c) return B2R_ERR_IN
 int b2r_last_kernel_ms(b2r_config* c, float* walk_ms, float* total_ms) {
     if (!c || !c->timing || c->device < 0) { set_error("timing is not enabled on this handle"); return B2R_ERR_INVALID_ARG; }
     DeviceGuard g(c->device);
-    CUDA_TRY(cudaEventSynchronize(c->ev[2]));
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
     if (walk_ms) CUDA_TRY(cudaEventElapsedTime(walk_ms, c->ev[0], c->ev[1]));
-    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[2]));
+    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[3]));
+    return B2R_OK;
+}
+int b2r_last_stage_ms(b2r_config* c, float* ms3) {
+    if (!c || !c->timing || c->device < 0 || !ms3) { set_error("timing is not enabled on this handle"); return B2R_ERR_INVALID_ARG; }
+    DeviceGuard g(c->device);
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventElapsedTime(ms3 + i, c->ev[i], c->ev[i + 1]));
+    return B2R_OK;
+}
+int b2r_last_plan(const b2r_config* c, uint32_t* table_mode, uint32_t* hist_mode) {
+    if (!c || !c->have_last) { set_error("no batch has been enqueued on this handle"); return B2R_ERR_INVALID_ARG; }
+    if (table_mode) *table_mode = c->last.table_mode;
+    if (hist_mode) *hist_mode = c->last.hist_mode;
     return B2R_OK;
 }
 

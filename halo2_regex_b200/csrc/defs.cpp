@@ -236,27 +236,21 @@ int pack_def(const AllstrDef& a, const std::vector<const SubstrDef*>& substrs, u
     return B2R_OK;
 }
 
-bool direct_table_applicable(const PackedDef* defs, uint32_t n_defs) {
-    if (n_defs == 0 || n_defs > 2) return false;   // shared memory: 64 KiB of table (+ bins) per def
-    for (uint32_t d = 0; d < n_defs; d++)
-        if (defs[d].num_states > 64 || defs[d].state_width != 1) return false;
-    return true;
+uint32_t padded_states(uint32_t num_states) {
+    uint32_t p = 1;
+    while (p < num_states + 1) p <<= 1;
+    return p;
 }
 
-void build_direct_table(const PackedDef* defs, uint32_t n_defs, std::vector<uint32_t>& out, uint32_t& hist_off) {
-    out.assign((size_t)n_defs * 256 * 65, 0u);
-    bool small = true;
-    for (uint32_t d = 0; d < n_defs; d++) {
-        const PackedDef& pd = defs[d];
-        small = small && pd.num_states <= 32;
-        for (uint32_t c = 0; c < 256; c++)
-            for (uint32_t s = 0; s < pd.num_states; s++) {
-                const uint32_t e = pd.trans[(size_t)pd.byte_class[c] * pd.num_states + s];
-                const uint32_t next = (e & ENT_INVALID) ? 0u : (e & ENT_NEXT_MASK);
-                out[(size_t)d * 256 * 65 + c * 65 + s] = (next << 2) | (next << 8) | (e & (ENT_SID_MASK | ENT_IS_START | ENT_IS_END | ENT_INVALID));
-            }
-    }
-    hist_off = small ? 128u : n_defs * 256u * 260u;
+void build_walk_table(const PackedDef& def, std::vector<uint32_t>& out) {
+    const uint32_t S = def.num_states, P = padded_states(S);
+    out.assign((size_t)def.num_classes * P, (S << 16) | 1u);
+    for (uint32_t k = 0; k < def.num_classes; k++)
+        for (uint32_t s = 0; s < S; s++) {
+            const uint32_t e = def.trans[(size_t)k * S + s];
+            if (e & ENT_INVALID) continue;
+            out[(size_t)k * P + s] = ((e & ENT_NEXT_MASK) << 16) | ((e & ENT_SID_MASK) ? 1u : 0u);
+        }
 }
 
 }  // namespace b2r

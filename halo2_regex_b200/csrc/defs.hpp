@@ -69,11 +69,11 @@ struct PackedDef {
     std::vector<uint32_t> erow_start_bin, erow_end_bin;
 };
 
-// Direct [256][64] table of the walk_direct kernel for n_defs defs with <= 64 states each (walk_direct.cuh):
-// entry(c,s) = next<<2 | next<<8 | substr_id<<16 | flags<<24 at u32 index d*16640 + c*65 + s (row stride 65 words); unused slots are 0.
-// hist_off = 128 when every def has <= 32 states (bins share the table rows), else n_defs*66560.
-bool direct_table_applicable(const PackedDef* defs, uint32_t n_defs);
-void build_direct_table(const PackedDef* defs, uint32_t n_defs, std::vector<uint32_t>& out, uint32_t& hist_off);
+// Walk table of walk_kernel (walk.cuh): [num_classes][P] with P = the power of two >= S + 1, entry = next << 16 | rare.
+// rare (bit 0) marks transitions with a non-zero substr id and invalid transitions; an invalid transition leads to the
+// trap state S (= the dummy state value), which only leads to itself.  Slots s >= S are trap rows.
+uint32_t padded_states(uint32_t num_states);
+void build_walk_table(const PackedDef& def, std::vector<uint32_t>& out);
 
 // returns 0, B2R_ERR_UNSUPPORTED or B2R_ERR_INVALID_ARG (message via set_error)
 int pack_def(const AllstrDef& a, const std::vector<const SubstrDef*>& substrs, uint32_t substr_id_offset, PackedDef& out);

@@ -1,12 +1,12 @@
-// Small kernels (multiplicity finalisation, failure diagnosis) and the walk_kernel launch dispatch.
-// The hot kernel itself lives in walk.cuh and is instantiated per number of defs in walk_inst.cu.
+// Small kernels (multiplicity finalisation, failure diagnosis) and the launch planning / dispatch of walk_kernel and
+// emit_kernel.  The two big kernels live in walk.cuh / emit.cuh and are instantiated per number of defs in walk_inst.cu.
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <cstdio>
 
+#include "emit.cuh"
 #include "walk.cuh"
-#include "walk_direct.cuh"
 
 namespace b2r {
 
@@ -45,87 +45,119 @@ __global__ void diagnose_kernel(const __grid_constant__ WalkParams p, uint64_t j
     *out = r;
 }
 
-// ---- launchers ---------------------------------------------------------------------------------------------------
-template <typename ST>
-static size_t per_warp_smem(int D) { return 32 * IN_PITCH + (size_t)D * 32 * StTile<ST>::PITCH; }
-
-int walk_smem_bytes(const WalkParams& p, bool wide, int warps, bool smem_tables, bool smem_hist) {
-    size_t n = 0;
-    for (uint32_t d = 0; d < p.n_defs; d++) {
-        if (smem_tables) n += (size_t)p.def[d].num_classes * p.def[d].num_states * 4 + 256;
-        if (smem_hist) n += (size_t)256 * p.def[d].num_states * 4;
-    }
-    n = (n + 15) & ~size_t(15);
-    n += sizeof(CtaCounters) + ((p.ep_smem_bytes + 15u) & ~15u);
-    n += (size_t)warps * (wide ? per_warp_smem<uint16_t>(p.n_defs) : per_warp_smem<uint8_t>(p.n_defs));
-    return (int)n;
+// ---- launch planning ---------------------------------------------------------------------------------------------------
+static int device_limits(int* n_sm, int* max_smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return B2R_ERR_CUDA; }
+    cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return B2R_OK;
 }
 
-template <> int launch_walk_d<1>(const WalkParams&, bool, bool, bool, size_t, int, cudaStream_t);
-template <> int launch_walk_d<2>(const WalkParams&, bool, bool, bool, size_t, int, cudaStream_t);
-template <> int launch_walk_d<3>(const WalkParams&, bool, bool, bool, size_t, int, cudaStream_t);
-template <> int launch_walk_d<4>(const WalkParams&, bool, bool, bool, size_t, int, cudaStream_t);
+static constexpr int MIN_WARPS_REPL = 8;   // below this the replicated tables are not worth the lost occupancy
 
-int launch_walk(const WalkParams& p, bool wide, void* stream, WalkLaunch* chosen) {
-    constexpr int WARPS = WALK_WARPS;
-    int dev = 0, n_sm = 0, max_smem = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    // shared-memory budget: tables first, then the histogram; fall back to global (L2) when they do not fit
-    bool ts = true, hs = true;
-    const int budget = max_smem / 2 - 1024;   // keep two CTAs per SM when possible
-    if (walk_smem_bytes(p, wide, WARPS, true, true) > budget) {
-        if (walk_smem_bytes(p, wide, WARPS, true, true) <= max_smem - 1024) { /* one CTA per SM */ }
-        else if (walk_smem_bytes(p, wide, WARPS, true, false) <= max_smem - 1024) hs = false;
-        else { ts = false; hs = false; }
+// Picks where the walk tables and the multiplicity bins live.  Preference: replicated tables + shared bins with as many
+// warps as possible; then a single copy of the tables; then global tables.  Bins go to shared memory whenever they fit.
+int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode) {
+    int n_sm = 0, max_smem = 0;
+    int rc = device_limits(&n_sm, &max_smem);
+    if (rc) return rc;
+    const uint32_t sb = wide ? 2 : 1;
+    auto fits = [&](uint32_t tm, uint32_t hm, int warps) {
+        p.table_mode = tm; p.hist_mode = hm;
+        if (tm != TABLE_GLOBAL) {
+            const uint32_t stride = walk_stride(tm);
+            for (uint32_t d = 0; d < p.n_defs; d++)
+                if ((uint64_t)p.def[d].padded_states * stride > 65536u) return false;   // entry bits [15:2] hold next*stride/4
+        }
+        uint64_t bins = 0;
+        for (uint32_t d = 0; d < p.n_defs; d++) bins += (uint64_t)(p.def[d].num_states + 1) * 1024u;
+        if (hm == HIST_SMEM && (wide || bins > (uint64_t)max_smem)) return false;
+        uint64_t tabs = 0;
+        if (tm != TABLE_GLOBAL)
+            for (uint32_t d = 0; d < p.n_defs; d++) tabs += (uint64_t)p.def[d].num_classes * p.def[d].padded_states * walk_stride(tm);
+        if (tabs > (uint64_t)max_smem) return false;
+        return walk_smem_bytes(p, sb, warps) <= (size_t)max_smem;
+    };
+    static const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {TABLE_PLAIN, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL},
+                                       {TABLE_PLAIN, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
+    for (const auto& o : order) {
+        if (force_table_mode >= 0 && (uint32_t)force_table_mode != o[0]) continue;   // testing hooks: honoured when they fit
+        if (force_hist_mode >= 0 && (uint32_t)force_hist_mode != o[1]) continue;
+        if (fits(o[0], o[1], 4)) return B2R_OK;
     }
-    const size_t smem = (size_t)walk_smem_bytes(p, wide, WARPS, ts, hs);
-    int per_sm = (int)((size_t)max_smem / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    long long want = ((long long)p.n_tiles + WARPS - 1) / WARPS;
-    int grid = n_sm * per_sm;
-    if (grid > want) grid = (int)(want > 0 ? want : 1);
-    if (chosen) { chosen->grid = grid; chosen->block = WARPS * 32; chosen->smem_bytes = smem; }
+    for (const auto& o : order) {
+        const int need = o[0] == TABLE_REPL ? MIN_WARPS_REPL : 4;
+        if (fits(o[0], o[1], need)) return B2R_OK;
+    }
+    set_error("walk_kernel: no table placement fits in shared memory");
+    return B2R_ERR_UNSUPPORTED;
+}
+
+template <int D>
+int launch_walk_d(const WalkParams& p, bool wide, size_t smem, int grid, int block, cudaStream_t st);
+template <> int launch_walk_d<1>(const WalkParams&, bool, size_t, int, int, cudaStream_t);
+template <> int launch_walk_d<2>(const WalkParams&, bool, size_t, int, int, cudaStream_t);
+template <> int launch_walk_d<3>(const WalkParams&, bool, size_t, int, int, cudaStream_t);
+template <> int launch_walk_d<4>(const WalkParams&, bool, size_t, int, int, cudaStream_t);
+template <int D>
+int launch_emit_d(const WalkParams& p, bool wide, size_t smem, int grid, cudaStream_t st);
+template <> int launch_emit_d<1>(const WalkParams&, bool, size_t, int, cudaStream_t);
+template <> int launch_emit_d<2>(const WalkParams&, bool, size_t, int, cudaStream_t);
+template <> int launch_emit_d<3>(const WalkParams&, bool, size_t, int, cudaStream_t);
+template <> int launch_emit_d<4>(const WalkParams&, bool, size_t, int, cudaStream_t);
+
+int launch_walk(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen) {
+    int n_sm = 0, max_smem = 0;
+    int rc = device_limits(&n_sm, &max_smem);
+    if (rc) return rc;
+    const uint32_t sb = wide ? 2 : 1;
+    int warps = WALK_MAX_THREADS / 32;
+    while (warps > 1 && walk_smem_bytes(p, sb, warps) > (size_t)max_smem) warps--;
+    const size_t smem = walk_smem_bytes(p, sb, warps);
+    if (smem > (size_t)max_smem) { set_error("walk_kernel: %zu bytes of shared memory needed, %d available", smem, max_smem); return B2R_ERR_UNSUPPORTED; }
+    // persistent: one CTA per SM; small batches use fewer CTAs
+    const long long ctas = ((long long)p.n_tiles + warps - 1) / warps;
+    const int grid = (int)(ctas < n_sm ? (ctas > 0 ? ctas : 1) : n_sm);
+    if (chosen) { chosen->grid = grid; chosen->block = warps * 32; chosen->smem_bytes = smem; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (p.n_defs) {
-        case 1: return launch_walk_d<1>(p, wide, ts, hs, smem, grid, st);
-        case 2: return launch_walk_d<2>(p, wide, ts, hs, smem, grid, st);
-        case 3: return launch_walk_d<3>(p, wide, ts, hs, smem, grid, st);
-        case 4: return launch_walk_d<4>(p, wide, ts, hs, smem, grid, st);
+        case 1: return launch_walk_d<1>(p, wide, smem, grid, warps * 32, st);
+        case 2: return launch_walk_d<2>(p, wide, smem, grid, warps * 32, st);
+        case 3: return launch_walk_d<3>(p, wide, smem, grid, warps * 32, st);
+        case 4: return launch_walk_d<4>(p, wide, smem, grid, warps * 32, st);
     }
     set_error("unsupported number of defs %u", p.n_defs);
     return B2R_ERR_UNSUPPORTED;
 }
 
-template <int D>
-int launch_direct_d(const WalkParams& p, const uint32_t* tab, bool in_row, size_t smem, int grid, int block, cudaStream_t st);
-template <> int launch_direct_d<1>(const WalkParams&, const uint32_t*, bool, size_t, int, int, cudaStream_t);
-template <> int launch_direct_d<2>(const WalkParams&, const uint32_t*, bool, size_t, int, int, cudaStream_t);
+size_t emit_smem_bytes(const WalkParams& p) {
+    size_t n = (p.ep_smem_bytes + 15u) & ~15u;
+    if (p.emit_smem_tables)
+        for (uint32_t d = 0; d < p.n_defs; d++) n += (size_t)p.def[d].num_classes * p.def[d].num_states * 4 + 256;
+    return n;
+}
 
-int launch_walk_direct(const WalkParams& p, const uint32_t* d_direct_tab, uint32_t hist_off, void* stream, WalkLaunch* chosen) {
-    int dev = 0, n_sm = 0, max_smem = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const uint32_t D = p.n_defs;
-    const bool in_row = hist_off == 128u;
-    const bool bins = p.want_hist && !in_row;
-    const size_t fixed = (size_t)D * DTAB_BYTES + (bins ? (size_t)D * DTAB_BYTES : 0) + ZERO_BYTES + sizeof(CtaCounters) + p.ep_smem_bytes;
-    const size_t per_warp = (size_t)direct_tile_bytes_per_warp((int)D);
-    int warps = (int)(((size_t)max_smem - fixed) / per_warp);
-    if (warps > DIRECT_MAX_THREADS / 32) warps = DIRECT_MAX_THREADS / 32;
-    if (warps < 1) { set_error("direct tables do not fit in shared memory"); return B2R_ERR_UNSUPPORTED; }
-    // persistent: one CTA per SM, tiles strided over (CTA, warp); small batches use fewer CTAs
-    long long ctas = ((long long)p.n_tiles + warps - 1) / warps;
-    int grid = (int)(ctas < n_sm ? (ctas > 0 ? ctas : 1) : n_sm);
-    const size_t smem = fixed + per_warp * warps;
-    if (chosen) { chosen->grid = grid; chosen->block = warps * 32; chosen->smem_bytes = smem; }
+int launch_emit(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen) {
+    int n_sm = 0, max_smem = 0;
+    int rc = device_limits(&n_sm, &max_smem);
+    if (rc) return rc;
+    const size_t smem = emit_smem_bytes(p);
+    const int wpc = EMIT_THREADS / 32;
+    int per_sm = 2048 / EMIT_THREADS;
+    if (smem) { const int by_smem = (int)((size_t)max_smem / (smem + 1024)); if (by_smem < per_sm) per_sm = by_smem < 1 ? 1 : by_smem; }
+    const long long want = ((long long)p.n_strings + wpc - 1) / wpc;
+    long long grid = (long long)n_sm * per_sm;
+    if (grid > want) grid = want > 0 ? want : 1;
+    if (chosen) { chosen->grid = (int)grid; chosen->block = EMIT_THREADS; chosen->smem_bytes = smem; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (D == 1) return launch_direct_d<1>(p, d_direct_tab, in_row, smem, grid, warps * 32, st);
-    if (D == 2) return launch_direct_d<2>(p, d_direct_tab, in_row, smem, grid, warps * 32, st);
-    set_error("direct kernel supports at most 2 defs");
+    switch (p.n_defs) {
+        case 1: return launch_emit_d<1>(p, wide, smem, (int)grid, st);
+        case 2: return launch_emit_d<2>(p, wide, smem, (int)grid, st);
+        case 3: return launch_emit_d<3>(p, wide, smem, (int)grid, st);
+        case 4: return launch_emit_d<4>(p, wide, smem, (int)grid, st);
+    }
+    set_error("unsupported number of defs %u", p.n_defs);
     return B2R_ERR_UNSUPPORTED;
 }
 

@@ -1,4 +1,9 @@
-// Device-side parameter blocks shared by kernels.cu and api.cu.
+// Device-side parameter blocks shared by the kernels (walk.cuh, emit.cuh, kernels.cu) and api.cu.
+//
+// The batch path is three launches:
+//   walk_kernel     (walk.cuh)   bytes -> state columns + one "granule flag" bit per 16 rows + multiplicity bins
+//   emit_kernel     (emit.cuh)   state columns + flags -> every other witness column, status, records, endpoint counters
+//   finalize_kernel (kernels.cu) dense bins -> multiplicities in the reference's table-row order
 #pragma once
 #include <cstdint>
 
@@ -7,10 +12,14 @@
 namespace b2r {
 
 struct DefDev {
+    // class-compressed tables of defs.hpp (emit + diagnose): entry = next | substr id | is_start | is_end | invalid
     const uint8_t* byte_class;       // [256]
-    const uint32_t* trans;           // [num_classes][num_states] packed entries (defs.hpp)
-    uint32_t num_states;             // S (= dummy state value)
+    const uint32_t* trans;           // [num_classes][num_states]
+    // walk table: [num_classes][padded_states], entry = next << 16 | rare (bit 0); next == num_states is the trap state
+    const uint32_t* hot;
+    uint32_t num_states;             // S (= dummy state value = trap state index)
     uint32_t num_classes;
+    uint32_t padded_states;          // P: power of two >= S + 1
     uint32_t first_state;
     uint32_t accepted_state;
     uint32_t sid_offset;
@@ -18,8 +27,8 @@ struct DefDev {
     unsigned long long* hist;        // dense [256][S] multiplicity bins (global, u64)
     unsigned long long* ep_start;    // [num_substrs][S] start-endpoint counters
     unsigned long long* ep_end;      // [num_substrs][S]
-    // outputs (may be null)
-    void* states;
+    // outputs
+    void* states;                    // never null inside the library (scratch column when the caller passes NULL)
     uint8_t* substr_ids;
     uint8_t* start_enable;
     uint8_t* end_enable;
@@ -29,8 +38,8 @@ struct BatchCounters {               // zeroed (first_bad = ~0) before every bat
     unsigned long long first_bad;    // lowest string index with an invalid transition / too long
     unsigned long long n_overlap;
     unsigned long long pad_rows;     // sum over strings of (M - len): multiplicity of table row 0
-    unsigned long long n_ok_strings; // strings that were walked to the end
-    unsigned long long tile_counter; // next tile of 32 strings to hand out (dynamic scheduling of the persistent CTAs)
+    unsigned long long n_ok_strings; // strings that were processed to the end
+    unsigned long long tile_counter; // next tile of 32 strings to hand out (dynamic scheduling of the persistent walk CTAs)
     unsigned long long reserved[3];
 };
 
@@ -51,12 +60,20 @@ struct WalkParams {
     uint32_t max_records, compact_pitch;
     BatchCounters* counters;
     uint32_t n_tiles;                // ceil(n_strings / 32)
-    uint32_t smem_tables;            // 1: class/transition tables staged in shared memory
-    uint32_t smem_hist;              // 1: multiplicity bins accumulated in shared memory, flushed with global atomics
-    uint32_t want_hist;              // 0: no multiplicity output was requested, skip the histogram
-    uint32_t* queue;                 // global scratch for the per-lane rare-row queues: grid*block lanes x queue_words(D) words
+    // granule flags: bit g of string j says rows [16g, 16g+16) contain a row with a non-zero substr id or an invalid
+    // transition in some def.  Word w of string j lives at fmask[w * n_strings + j]; fm_words = ceil(ceil((M-1)/16) / 32).
+    uint32_t* fmask;
+    uint32_t fm_words;
+    uint32_t table_mode;             // TABLE_REPL / TABLE_PLAIN / TABLE_GLOBAL (walk.cuh)
+    uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
+    uint32_t emit_smem_tables;       // 1: emit_kernel stages byte_class / trans in shared memory
 };
+
+constexpr uint32_t TABLE_REPL = 0;   // shared memory, one copy of every entry per bank (stride 128 B): conflict-free lookups
+constexpr uint32_t TABLE_PLAIN = 1;  // shared memory, one copy (stride 4 B)
+constexpr uint32_t TABLE_GLOBAL = 2; // global memory (L1/L2)
+constexpr uint32_t HIST_NONE = 0, HIST_SMEM = 1, HIST_GLOBAL = 2;
 
 struct FinalizeParams {
     uint32_t n_defs;
@@ -75,16 +92,17 @@ struct FinalizeParams {
     } def[B2R_MAX_DEFS];
 };
 
-struct WalkLaunch {
+struct LaunchInfo {
     int grid, block;
     size_t smem_bytes;
 };
 
-// host-callable launchers (kernels.cu)
-int launch_walk(const WalkParams& p, bool wide_states, void* stream, WalkLaunch* chosen);
+// host-callable launchers (kernels.cu / walk_inst.cu)
+// chooses table_mode / hist_mode for this device (force_* >= 0: preferred placement, testing hook); 0 or an error
+int plan_walk(WalkParams& p, bool wide_states, int force_table_mode, int force_hist_mode);
+int launch_walk(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);
+int launch_emit(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);
 int launch_finalize(const FinalizeParams& p, void* stream);
 int launch_diagnose(const WalkParams& p, uint64_t string_idx, b2r_batch_status* d_out, void* stream);
-int launch_walk_direct(const WalkParams& p, const uint32_t* d_direct_tab, uint32_t hist_off, void* stream, WalkLaunch* chosen);
-int walk_smem_bytes(const WalkParams& p, bool wide_states, int warps, bool smem_tables, bool smem_hist);
 
 }  // namespace b2r

@@ -1,362 +1,384 @@
-// walk_kernel — the hot kernel of the DFA witness-generation path (sm_100a).
+// walk_kernel — stage 1 of the batch path: the DFA walk (reference derive_states, src/lib.rs:804-823).
 //
-// One LANE per string, one WARP per tile of 32 strings:
-//   * the input bytes of the tile's 32 strings are staged chunk by chunk (CH positions) into a padded shared-memory
-//     tile with 16-byte coalesced global loads, so that each lane then reads ITS string with conflict-free LDS.128;
-//   * each lane walks its DFA(s) sequentially: one packed-entry lookup per byte per def in the shared-memory
-//     class/transition tables (entry = next state | substr id | is_start | is_end | invalid, see defs.hpp), which replaces
-//     derive_states + derive_substr_ids + derive_is_start_end of the reference (src/lib.rs:804-888);
-//   * the state column is transposed back through shared memory and stored with 16-byte coalesced stores; the sparse
-//     columns (substr ids, start/end enable bitmaps, masked chars / ids) are zero-filled with coalesced stores and
-//     patched by the owning lane only where they are non-zero (out-of-line "rare row" path);
-//   * the start_mask/end_mask scans of the reference (src/lib.rs:598-714) are evaluated in closed form: events happen
-//     only at boundaries where the id sum changes and is_start/is_end is set; mask = 1 exactly on the stretch between
-//     an event with is_start and the NEXT event when that one has is_end (DESIGN.md "mask algebra");
-//   * lookup-input multiplicities are accumulated per (byte, state) in a shared-memory histogram and flushed with
-//     global 64-bit atomics (table row r <-> bin via PackedDef::row_bin).
+// One LANE per string, one WARP per tile of 32 strings, persistent CTAs (one per SM), tiles handed out by an atomic
+// counter.  The kernel produces
+//   - the state column of every def (rows 0..len-1 = s_i, row len = final state, later rows = dummy, src/lib.rs:404-418),
+//   - one flag bit per 16-row granule and string: "some row in here has a non-zero substr id or an invalid transition"
+//     (everything the reference derives beyond the state column lives in such rows; emit.cuh re-derives it from the
+//     state column, only inside flagged granules),
+//   - the multiplicity bins of the transition lookup (src/lib.rs:207-233): one count per (byte, state) row.
+// There is no data-dependent branch in the hot loop.
+//
+// Tables.  The sparse lookup text was packed by defs.cpp into byte classes + a [class][state] next-state table.  In
+// shared memory every entry is REPLICATED ONCE PER BANK (TABLE_REPL): entry (class k, state s) of lane l lives at
+//   tab + (k*P + s)*128 + l*4,
+// so a warp's 32 lookups (32 different strings, arbitrary bytes and states) never conflict: one wavefront per lookup
+// instead of ~3.4 for randomly banked addresses.  The byte -> class table is replicated the same way and, for a single
+// def, holds the ABSOLUTE shared address of (class row, state 0, this lane).  An entry is
+//   [31:16] next state   [15:2] next state * stride / 4   [0] rare
+// so the dependent chain per byte is   LOP3 (entry & 0xFFFC | class row)  ->  LDS.
+// When the replicated tables do not fit, the same code runs with stride 4 (TABLE_PLAIN, one copy, bank conflicts), and
+// when even that does not fit the table stays in global memory (TABLE_GLOBAL, template parameter).
+//
+// I/O.  cp.async 16-byte copies (zero-filled past the string end) stage chunk k+1 of the 32 strings into a padded,
+// double-buffered tile while chunk k is walked; each lane reads ITS string with conflict-free LDS.128.  States go back
+// through a padded tile and out as coalesced 16-byte stores, one full 32-byte sector per row and chunk.
+//
+// Multiplicities.  One shared-memory atomic per byte into bins [state][byte] (bank = byte mod 32), flushed once per
+// CTA with 64-bit global atomics.  (HIST_GLOBAL: straight to the global bins; only for tables too large for shared memory.)
 #pragma once
-#include "rare.cuh"
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "defs.hpp"
+#include "kernels.cuh"
 
 namespace b2r {
 
-constexpr int CH = 64;              // positions per staged chunk
-constexpr int IN_PITCH = CH + 16;   // +1 vector for unaligned strings; 5 x 16 B keeps LDS.128 conflict-free
+constexpr int WALK_MAX_THREADS = 512;
+constexpr int WALK_DCH = 32;                       // positions per staged chunk
+constexpr int WALK_PITCH = WALK_DCH + 16;          // input tile row pitch (bytes): 3 x 16 B keeps per-lane LDS.128 conflict-free
 
-template <typename ST>
-struct StTile {
-    static constexpr int ROW_BYTES = CH * (int)sizeof(ST);
-    static constexpr int PITCH = ROW_BYTES + 16;        // odd multiple of 16 B
-    static constexpr int VPR = ROW_BYTES / 16;          // vectors per row
+// ---- PTX helpers -------------------------------------------------------------------------------------------------------
+// prmt (default mode): selector nibble 0-7 picks a byte of {a (0-3), b (4-7)}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t saddr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory"); }
+// 16-byte async copy global -> shared; copies src_bytes (0 or 16) and zero-fills the rest
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- shared-memory layout, computed identically by the launcher and the kernel ---------------------------------------------
+__host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : 4u; }
+__host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
+
+struct WalkLayout {
+    uint32_t tab[B2R_MAX_DEFS];    // byte offsets from the aligned base; table rows are P*stride bytes and aligned to that
+    uint32_t cls;                  // 256 entries of `stride` bytes
+    uint32_t hist[B2R_MAX_DEFS];   // (S+1) x 256 u32 bins per def
+    uint32_t tiles;                // first per-warp tile
+    uint32_t per_warp;
+    uint32_t align;                // alignment the base needs (the largest table row)
 };
-
-// one rare row handled immediately, out of line (class-compressed entry encoding: next state in bits 0..15)
-template <int D>
-__device__ __noinline__ void rare_row_generic(const WalkParams& p, const Cold<D, 1>& k, const RowCtx<D, ClassTables>& x, uint32_t pos, const uint32_t* e,
-                                              const uint32_t* s, uint32_t* expect) {
-    uint32_t nx[D], run_sid[D];
-#pragma unroll
-    for (int d = 0; d < D; d++) { nx[d] = e[d] & ENT_NEXT_MASK; run_sid[d] = expect[d] >> 16; }
-    (void)nx; (void)run_sid;
-    push_row<D, 1, ClassTables>(p, k, x, pos, e, s);
-#pragma unroll
-    for (int d = 0; d < D; d++) expect[d] = e[d] & ENT_SID_MASK;
+__host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t state_bytes) {
+    WalkLayout L{};
+    uint32_t cur = 0, al = 128;
+    if (p.table_mode != TABLE_GLOBAL) {
+        const uint32_t stride = walk_stride(p.table_mode);
+        for (uint32_t d = 0; d < p.n_defs; d++) {
+            const uint32_t rb = p.def[d].padded_states * stride;
+            cur = walk_align_up(cur, rb);
+            L.tab[d] = cur;
+            cur += p.def[d].num_classes * rb;
+            if (rb > al) al = rb;
+        }
+        cur = walk_align_up(cur, 128);
+        L.cls = cur;
+        cur += 256 * stride;
+    }
+    if (p.hist_mode == HIST_SMEM)
+        for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
+    cur = walk_align_up(cur, 16);
+    L.tiles = cur;
+    L.per_warp = 2 * 32 * WALK_PITCH + p.n_defs * 32 * (WALK_DCH * state_bytes + 16);
+    L.align = al;
+    return L;
+}
+__host__ __device__ inline size_t walk_smem_bytes(const WalkParams& p, uint32_t state_bytes, int warps) {
+    const WalkLayout L = walk_layout(p, state_bytes);
+    return (size_t)L.align + L.tiles + (size_t)warps * L.per_warp;   // + align: the dynamic base is only 16-byte aligned
 }
 
-template <int D, typename ST, bool TBL_SMEM, bool HIST_SMEM, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) walk_kernel(const __grid_constant__ WalkParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// TM: TABLE_REPL (also runs TABLE_PLAIN: the stride is a run-time value) or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
+template <int D, typename ST, int TM, int HM>
+__global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_constant__ WalkParams p) {
+    constexpr int DCH = WALK_DCH, PITCH = WALK_PITCH;
+    constexpr int SB = sizeof(ST);
+    constexpr int SPITCH = DCH * SB + 16;        // state tile row pitch
+    constexpr int VPR = DCH / 16;                // input vectors per row and chunk
+    constexpr int VPS = DCH * SB / 16;           // state vectors per row and chunk
+    constexpr bool SMEM_TAB = TM != (int)TABLE_GLOBAL;
+    extern __shared__ __align__(16) unsigned char dsmem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
-    // ---- shared memory carve-up ------------------------------------------------------------------------------
-    unsigned char* sp = smem;
-    const uint8_t* cls_t[D];
-    const uint32_t* trans_t[D];
-    uint32_t* hist_t[D];
-    uint32_t S_[D];
+    const WalkLayout lay = walk_layout(p, SB);
+    const uint32_t base_s = (smem_u32(dsmem) + lay.align - 1) & ~(lay.align - 1);
+    const uint32_t stride = SMEM_TAB ? walk_stride(p.table_mode) : 0u;
+    const uint32_t laneoff = (SMEM_TAB && p.table_mode == TABLE_REPL) ? (uint32_t)lane * 4u : 0u;
+
+    // ---- stage the tables ----------------------------------------------------------------------------------------------
+    if (SMEM_TAB) {
+        const uint32_t csh = p.table_mode == TABLE_REPL ? 5u : 0u;   // log2(copies)
 #pragma unroll
-    for (int d = 0; d < D; d++) {
-        S_[d] = p.def[d].num_states;
-        if (TBL_SMEM) {
-            uint32_t* tr = reinterpret_cast<uint32_t*>(sp);
-            const uint32_t n = p.def[d].num_classes * S_[d];
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) tr[i] = p.def[d].trans[i];
-            sp += (size_t)n * 4;
-            uint8_t* cl = sp;
-            for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cl[i] = p.def[d].byte_class[i];
-            sp += 256;
-            trans_t[d] = tr; cls_t[d] = cl;
-        } else {
-            trans_t[d] = p.def[d].trans; cls_t[d] = p.def[d].byte_class;
+        for (int d = 0; d < D; d++) {
+            const uint32_t n = p.def[d].num_classes * p.def[d].padded_states;
+            const uint32_t t0 = base_s + lay.tab[d];
+            for (uint32_t i = threadIdx.x; i < (n << csh); i += blockDim.x) {
+                const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u);
+                const uint32_t e = __ldg(p.def[d].hot + idx);
+                sts32(t0 + idx * stride + l * 4, e | ((e >> 16) * stride));
+            }
         }
-        if (HIST_SMEM) {
-            uint32_t* h = reinterpret_cast<uint32_t*>(sp);
-            const uint32_t n = 256u * S_[d];
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) h[i] = 0;
-            sp += (size_t)n * 4;
-            hist_t[d] = h;
-        } else hist_t[d] = nullptr;
+        for (uint32_t i = threadIdx.x; i < (256u << csh); i += blockDim.x) {
+            const uint32_t c = i >> csh, l = i & ((1u << csh) - 1u);
+            uint32_t v;
+            if (D == 1) {
+                v = base_s + lay.tab[0] + (uint32_t)__ldg(p.def[0].byte_class + c) * p.def[0].padded_states * stride + l * 4;
+            } else {
+                v = 0;
+#pragma unroll
+                for (int d = 0; d < D; d++) v |= (uint32_t)__ldg(p.def[d].byte_class + c) << (8 * d);
+            }
+            sts32(base_s + lay.cls + c * stride + l * 4, v);
+        }
     }
-    sp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
-    CtaCounters* const cc = reinterpret_cast<CtaCounters*>(sp);
-    unsigned char* const ep_base = sp + sizeof(CtaCounters);
-    uint32_t* ep_s[D];
-    ep_smem_layout<D>(p, ep_base, ep_s);
-    cta_counters_init<D>(p, ep_base, cc);
-    sp = ep_base + ((p.ep_smem_bytes + 15u) & ~15u);
-    unsigned char* in_tile = sp + (size_t)warp * (32 * IN_PITCH + D * 32 * StTile<ST>::PITCH);
-    unsigned char* st_tile = in_tile + 32 * IN_PITCH;
+    if (HM == (int)HIST_SMEM) {
+#pragma unroll
+        for (int d = 0; d < D; d++)
+            for (uint32_t i = threadIdx.x; i < (p.def[d].num_states + 1) * 256u; i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
+    }
     __syncthreads();
 
     const uint32_t M = p.max_chars;
-    const uint32_t Mpad = (M + 15u) & ~15u;                 // rows written (row_pitch >= Mpad by contract)
-    const uint32_t n_chunks = (Mpad + CH - 1) / CH;
+    const uint32_t Mpad = (M + 15u) & ~15u;                             // rows written (row_pitch >= Mpad by contract)
+    const uint32_t n_chunks = (Mpad + DCH - 1) / DCH;
     const uint64_t rp = p.row_pitch;
-    const bool want_hist = p.want_hist != 0;
+    const uint32_t cls_lane_s = base_s + lay.cls + laneoff;
+    uint32_t tabl[D], rowb[D], hist_s[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        tabl[d] = base_s + lay.tab[d] + laneoff;
+        rowb[d] = p.def[d].padded_states * stride;
+        hist_s[d] = base_s + lay.hist[d];
+    }
+    const uint32_t in_s = base_s + lay.tiles + (uint32_t)warp * lay.per_warp;
+    const uint32_t st_s = in_s + 2 * 32 * PITCH;
+    const int kv = lane % VPR, r0 = lane / VPR;                         // input staging: vector kv of rows r0 + (32/VPR)*i
+    const int skv = lane % VPS, sr0 = lane / VPS;                       // state store:   vector skv of rows sr0 + (32/VPS)*i
 
-    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < p.n_tiles; tile += gridDim.x * WARPS) {
-        const uint64_t tile_base = (uint64_t)tile * 32;
+    // one position of def d: `cur` is the entry that led to the current state, c the byte.  Returns the next entry.
+    auto lookup = [&](int d, uint32_t cur, uint32_t c, uint32_t cent) -> uint32_t {
+        if (SMEM_TAB) {
+            const uint32_t row = (D == 1) ? cent : tabl[d] + ((cent >> (8 * d)) & 0xFFu) * rowb[d];
+            return lds32((cur & 0xFFFCu) | row);
+        } else {
+            const uint32_t k = __ldg(p.def[d].byte_class + c);
+            return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> 16));
+        }
+    };
+    auto count = [&](int d, uint32_t cur, uint32_t c) {
+        if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> 16) << 8) | c) * 4);
+        else {
+            const uint32_t s = cur >> 16;
+            if (s < p.def[d].num_states) atomicAdd(p.def[d].hist + (size_t)c * p.def[d].num_states + s, 1ull);
+        }
+    };
+
+    for (;;) {
+        unsigned long long t64 = 0;
+        if (lane == 0) t64 = atomicAdd(&p.counters->tile_counter, 1ull);
+        t64 = __shfl_sync(0xffffffffu, t64, 0);
+        if (t64 >= p.n_tiles) break;
+        const uint64_t tile_base = t64 * 32;
         const uint64_t idx = tile_base + lane;
         const bool valid = idx < p.n_strings;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[idx]; end = p.offsets[idx + 1]; }
-        uint32_t cold_store[cold_fields(D)];                              // cold state in local memory (stride 1)
-        const Cold<D, 1> k{cold_store};
-        bool dead = !valid;
-        if (valid && (end < off || end - off > (uint64_t)(M - 1))) {     // len must be <= M-1
-            dead = true; end = off;
-            kill_string(p, idx);
-        }
+        if (end < off || end - off > (uint64_t)(M - 1)) end = off;      // too long: emit reports it; walk nothing
         const uint32_t L = (uint32_t)(end - off);
-        k.init();
-        RowCtx<D, ClassTables> x;
-        x.idx = idx; x.src = p.bytes + off; x.len = L; x.tile_pos = NO_POS; x.tile_s = 0;
-        x.qbase = p.queue + ((size_t)(blockIdx.x * WARPS + warp) * queue_words(D)) * 32 + lane;
-        uint32_t s[D], expect[D];
+        const uint32_t rows_here = (p.n_strings - tile_base < 32) ? (uint32_t)(p.n_strings - tile_base) : 32u;
+
+        uint32_t cur[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            s[d] = p.def[d].first_state; expect[d] = 0;
-            x.tb[d].cls = cls_t[d]; x.tb[d].trans = trans_t[d]; x.tb[d].S = S_[d]; x.ep_s[d] = ep_s[d];
-        }
-        const uint64_t abase = off & ~uint64_t(15);
+        for (int d = 0; d < D; d++) cur[d] = (p.def[d].first_state << 16) | (p.def[d].first_state * stride);
+
+        // staging geometry
         const uint32_t shift = (uint32_t)(off & 15);
         const bool any_shift = __any_sync(0xffffffffu, shift != 0);
-
-        // zero the tile's bitmap rows (32 adjacent rows are contiguous)
+        const uint8_t* in_ptr[VPR];                                     // vector kv of chunk 0 of row r0 + (32/VPR)*i
+        uint32_t in_left[VPR];                                          // bytes from there to the end of that string
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint64_t nrows = (p.n_strings - tile_base < 32) ? (p.n_strings - tile_base) : 32;
-            const uint64_t words = nrows * p.bitmap_pitch / 4;
-            if (p.def[d].start_enable) {
-                uint32_t* w = reinterpret_cast<uint32_t*>(p.def[d].start_enable + tile_base * p.bitmap_pitch);
-                for (uint64_t i = lane; i < words; i += 32) w[i] = 0;
-            }
-            if (p.def[d].end_enable) {
-                uint32_t* w = reinterpret_cast<uint32_t*>(p.def[d].end_enable + tile_base * p.bitmap_pitch);
-                for (uint64_t i = lane; i < words; i += 32) w[i] = 0;
-            }
+        for (int i = 0; i < VPR; i++) {
+            const int row = r0 + (32 / VPR) * i;
+            const uint64_t roff = __shfl_sync(0xffffffffu, off, row);
+            const uint64_t rend = __shfl_sync(0xffffffffu, end, row);
+            const uint64_t a = (roff & ~uint64_t(15)) + (uint32_t)kv * 16;
+            in_ptr[i] = p.bytes + a;
+            in_left[i] = rend > a ? (uint32_t)(rend - a) : 0u;
         }
+        const uint64_t tail_a = (off & ~uint64_t(15)) + DCH;            // extra vector of this lane's own row (unaligned strings)
+        const uint8_t* const my_tail = p.bytes + tail_a;
+        const uint32_t my_tail_left = end > tail_a ? (uint32_t)(end - tail_a) : 0u;
 
-        // ---- chunk loop ------------------------------------------------------------------------------------------
+        auto stage = [&](uint32_t chunk) {   // async copy of chunk `chunk` into input tile (chunk & 1)
+            const uint32_t cbase = chunk * DCH;
+            const uint32_t dst = in_s + (chunk & 1) * (32 * PITCH) + kv * 16;
+#pragma unroll
+            for (int i = 0; i < VPR; i++) cp_async16(dst + (r0 + (32 / VPR) * i) * PITCH, in_ptr[i] + cbase, cbase < in_left[i] ? 16u : 0u);
+            if (any_shift) cp_async16(in_s + (chunk & 1) * (32 * PITCH) + lane * PITCH + DCH, my_tail + cbase, cbase < my_tail_left ? 16u : 0u);
+            cp_async_commit();
+        };
+        stage(0);
+
+        uint32_t fm = 0;                                                // granule flags of the current group of 32 granules
 #pragma unroll 1
         for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
-            const uint32_t cbase = chunk * CH;
-            // (1) stage the input chunk: rows of 4 (aligned tile) or 5 vectors starting at the 16-byte aligned string base
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                const int v = lane + 32 * i;
-                const int row = any_shift ? v / 5 : v >> 2;
-                const int kk = any_shift ? v - row * 5 : v & 3;
-                const uint64_t rbase = __shfl_sync(0xffffffffu, abase, row & 31);
-                const uint64_t rend = __shfl_sync(0xffffffffu, end, row & 31);
-                if (row < 32) {
-                    const uint64_t g = rbase + cbase + (uint32_t)kk * 16;
-                    uint4 val = make_uint4(0, 0, 0, 0);
-                    if (g < rend) val = *reinterpret_cast<const uint4*>(p.bytes + g);
-                    *reinterpret_cast<uint4*>(in_tile + row * IN_PITCH + kk * 16) = val;
-                }
-            }
-            // (2) zero-fill the sparse byte columns of this chunk (coalesced, straight from registers)
-            {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int v = lane + 32 * i;
-                    const int row = v >> 2, kk = v & 3;
-                    const uint32_t col = cbase + kk * 16;
-                    if (tile_base + row < p.n_strings && col < Mpad) {
-                        const uint64_t o = (tile_base + row) * rp + col;
-                        if (p.masked_chars) *reinterpret_cast<uint4*>(p.masked_chars + o) = z;
-                        if (p.masked_substr_ids) *reinterpret_cast<uint4*>(p.masked_substr_ids + o) = z;
-#pragma unroll
-                        for (int d = 0; d < D; d++)
-                            if (p.def[d].substr_ids) *reinterpret_cast<uint4*>(p.def[d].substr_ids + o) = z;
-                    }
-                }
-            }
+            const uint32_t cbase = chunk * DCH;
+            if (chunk + 1 < n_chunks) { stage(chunk + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
             __syncwarp();
 
-            // (3) walk: this lane's string, positions [cbase, cbase+CH)
-            const unsigned char* my_in = in_tile + lane * IN_PITCH;
+            const uint32_t my_in = in_s + (chunk & 1) * (32 * PITCH) + lane * PITCH;
 #pragma unroll 1
-            for (int g = 0; g < CH / 16; g++) {
+            for (int g = 0; g < DCH / 16; g++) {
                 const uint32_t gbase = cbase + g * 16;
+                if (gbase >= Mpad) break;
                 uint32_t w[4];
                 if (!any_shift) {
-                    const uint4 t = *reinterpret_cast<const uint4*>(my_in + g * 16);
-                    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+                    const uint4 v = lds128(my_in + g * 16);
+                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
                 } else {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(my_in + g * 16 + (shift & ~3u));
+                    const uint32_t q = my_in + g * 16 + (shift & ~3u);
                     const uint32_t sh = (shift & 3u) * 8;
-                    const uint32_t x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], x4 = q[4];
+                    const uint32_t x0 = lds32(q), x1 = lds32(q + 4), x2 = lds32(q + 8), x3 = lds32(q + 12), x4 = lds32(q + 16);
                     w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh);
                     w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
                 }
-                ST pk[D][16];
-                if (gbase + 16 <= L && !dead) {
-                    // all 16 rows are real characters
+                uint32_t pk[D][4 * SB];
+                uint32_t acc = 0;
+                if (gbase + 16 <= L) {
+                    // ---- hot path: 16 real characters, no data-dependent branch ---------------------------------------
 #pragma unroll
-                    for (int b = 0; b < 16; b++) {
-                        const uint32_t c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
-                        uint32_t e[D];
-                        uint32_t rare = 0;
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t held[D];                               // u16 states: entry of the even position
 #pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            if (TBL_SMEM) e[d] = trans_t[d][(uint32_t)cls_t[d][c] * S_[d] + s[d]];
-                            else e[d] = __ldg(trans_t[d] + (uint32_t)__ldg(cls_t[d] + c) * S_[d] + s[d]);
-                            if (want_hist) {
-                                if (HIST_SMEM) atomicAdd(hist_t[d] + c * S_[d] + s[d], 1u);
-                                else atomicAdd(p.def[d].hist + c * S_[d] + s[d], 1ull);
-                            }
-                            pk[d][b] = (ST)s[d];
-                            rare |= (e[d] ^ expect[d]) & ENT_RARE_MASK;
-                        }
-                        if (rare) {   // only copies escape to the out-of-line call: s/e/expect stay in registers
-                            uint32_t inval = 0;
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t c = prmt(w[q], 0u, 0x4440u + j);
+                            uint32_t cent = 0;
+                            if (SMEM_TAB) cent = lds32(cls_lane_s + c * stride);
 #pragma unroll
-                            for (int d = 0; d < D; d++) inval |= e[d] & ENT_INVALID;
-                            if (inval) { if (!dead) { dead = true; kill_string(p, idx); } }
-                            else if (!dead) {
-                                uint32_t te[D], ts[D], tx[D];
-#pragma unroll
-                                for (int d = 0; d < D; d++) { te[d] = e[d]; ts[d] = s[d]; tx[d] = expect[d]; }
-                                rare_row_generic<D>(p, k, x, gbase + b, te, ts, tx);
-#pragma unroll
-                                for (int d = 0; d < D; d++) expect[d] = tx[d];
+                            for (int d = 0; d < D; d++) {
+                                const uint32_t e = lookup(d, cur[d], c, cent);
+                                count(d, cur[d], c);
+                                if (SB == 1) {                          // state byte (cur byte 2) into byte j of the pack
+                                    const uint32_t sel = j == 0 ? 0x3216u : j == 1 ? 0x3260u : j == 2 ? 0x3610u : 0x6210u;
+                                    pk[d][q] = prmt(j == 0 ? 0u : pk[d][q], cur[d], sel);
+                                } else {
+                                    if ((j & 1) == 0) held[d] = cur[d];
+                                    else pk[d][q * 2 + (j >> 1)] = prmt(held[d], cur[d], 0x7632u);
+                                }
+                                acc |= e;
+                                cur[d] = e;
                             }
                         }
-#pragma unroll
-                        for (int d = 0; d < D; d++) s[d] = e[d] & ENT_NEXT_MASK;
                     }
                 } else {
-                    // ragged end: characters, then the final-state row, then dummy rows
+                    // ---- ragged end: characters, then the final-state row, then dummy rows -------------------------
+#pragma unroll
+                    for (int d = 0; d < D; d++)
+#pragma unroll
+                        for (int i = 0; i < 4 * SB; i++) pk[d][i] = 0;
+                    uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];   // shifted along: no dynamic register indexing
 #pragma unroll 1
                     for (int b = 0; b < 16; b++) {
                         const uint32_t pos = gbase + b;
-                        const uint32_t c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
-                        if (pos < L && !dead) {
-                            uint32_t e[D];
-                            uint32_t rare = 0;
+                        const uint32_t c = v0 & 0xFFu;
+                        v0 = __funnelshift_r(v0, v1, 8); v1 = __funnelshift_r(v1, v2, 8); v2 = __funnelshift_r(v2, v3, 8); v3 >>= 8;
+                        uint32_t cent = 0;
+                        if (SMEM_TAB && pos < L) cent = lds32(cls_lane_s + c * stride);
 #pragma unroll
-                            for (int d = 0; d < D; d++) {
-                                if (TBL_SMEM) e[d] = trans_t[d][(uint32_t)cls_t[d][c] * S_[d] + s[d]];
-                                else e[d] = __ldg(trans_t[d] + (uint32_t)__ldg(cls_t[d] + c) * S_[d] + s[d]);
-                                if (want_hist) {
-                                    if (HIST_SMEM) atomicAdd(hist_t[d] + c * S_[d] + s[d], 1u);
-                                    else atomicAdd(p.def[d].hist + c * S_[d] + s[d], 1ull);
-                                }
-                                rare |= (e[d] ^ expect[d]) & ENT_RARE_MASK;
+                        for (int d = 0; d < D; d++) {
+                            const uint32_t stv = (pos <= L) ? (cur[d] >> 16) : p.def[d].num_states;   // state, final state, then dummy
+                            if (pos < L) {
+                                const uint32_t e = lookup(d, cur[d], c, cent);
+                                count(d, cur[d], c);
+                                acc |= e;
+                                cur[d] = e;
                             }
-                            // state byte goes straight to the tile (dynamic b: no register array indexing)
+                            // insert stv at element b of the pack: rotate the pack down by one element, put stv on top
+                            if (SB == 1) {
+                                pk[d][0] = __funnelshift_r(pk[d][0], pk[d][1], 8); pk[d][1] = __funnelshift_r(pk[d][1], pk[d][2], 8);
+                                pk[d][2] = __funnelshift_r(pk[d][2], pk[d][3], 8); pk[d][3] = (pk[d][3] >> 8) | (stv << 24);
+                            } else {
 #pragma unroll
-                            for (int d = 0; d < D; d++)
-                                reinterpret_cast<ST*>(st_tile + (d * 32 + lane) * StTile<ST>::PITCH)[g * 16 + b] = (ST)s[d];
-                            if (rare) {
-                                uint32_t inval = 0;
-#pragma unroll
-                                for (int d = 0; d < D; d++) inval |= e[d] & ENT_INVALID;
-                                if (inval) { dead = true; kill_string(p, idx); }
-                                else {
-                                    uint32_t te[D], ts[D], tx[D];
-#pragma unroll
-                                    for (int d = 0; d < D; d++) { te[d] = e[d]; ts[d] = s[d]; tx[d] = expect[d]; }
-                                    rare_row_generic<D>(p, k, x, pos, te, ts, tx);
-#pragma unroll
-                                    for (int d = 0; d < D; d++) expect[d] = tx[d];
-                                }
-                            }
-                            if (!dead) {
-#pragma unroll
-                                for (int d = 0; d < D; d++) s[d] = e[d] & ENT_NEXT_MASK;
-                            }
-                        } else {
-#pragma unroll
-                            for (int d = 0; d < D; d++)
-                                reinterpret_cast<ST*>(st_tile + (d * 32 + lane) * StTile<ST>::PITCH)[g * 16 + b] = (ST)((pos <= L) ? s[d] : S_[d]);  // final state, then dummy
-                            if (pos == L && !dead) {
-                                uint32_t ts[D];
-#pragma unroll
-                                for (int d = 0; d < D; d++) ts[d] = s[d];
-                                finish_string<D, 1, ClassTables>(p, k, x, ts);
+                                for (int i = 0; i < 7; i++) pk[d][i] = __funnelshift_r(pk[d][i], pk[d][i + 1], 16);
+                                pk[d][7] = (pk[d][7] >> 16) | (stv << 16);
                             }
                         }
                     }
-                    continue;   // tile bytes already written
                 }
 #pragma unroll
                 for (int d = 0; d < D; d++) {
-                    unsigned char* dst = st_tile + (d * 32 + lane) * StTile<ST>::PITCH + g * 16 * (int)sizeof(ST);
-                    if (sizeof(ST) == 1) {
-                        uint32_t r[4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            r[q] = (uint32_t)pk[d][4 * q] | ((uint32_t)pk[d][4 * q + 1] << 8) | ((uint32_t)pk[d][4 * q + 2] << 16) | ((uint32_t)pk[d][4 * q + 3] << 24);
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
-                    } else {
-                        uint32_t r[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) r[q] = (uint32_t)pk[d][2 * q] | ((uint32_t)pk[d][2 * q + 1] << 16);
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
-                        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(r[4], r[5], r[6], r[7]);
-                    }
+                    const uint32_t a = st_s + (d * 32 + lane) * SPITCH + g * 16 * SB;
+                    sts128(a, pk[d][0], pk[d][1], pk[d][2], pk[d][3]);
+                    if (SB == 2) sts128(a + 16, pk[d][4], pk[d][5], pk[d][6], pk[d][7]);
                 }
+                const uint32_t gi = (cbase >> 4) + g;                   // granule index
+                if (acc & 1u) fm |= 1u << (gi & 31);
             }
             __syncwarp();
 
-            // (4) store the state tile (coalesced 16-byte vectors)
+            // store the state tile: coalesced 16-byte vectors, one 32-byte sector (u8) per row
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                if (!p.def[d].states) continue;
-                constexpr int VPR = StTile<ST>::VPR;
+                uint8_t* const col = reinterpret_cast<uint8_t*>(p.def[d].states);
 #pragma unroll
-                for (int i = 0; i < VPR; i++) {
-                    const int v = lane + 32 * i;
-                    const int row = v / VPR, kk = v % VPR;
-                    const uint32_t col = cbase + kk * (16 / (int)sizeof(ST));
-                    if (tile_base + row < p.n_strings && col < Mpad) {
-                        const uint4 val = *reinterpret_cast<const uint4*>(st_tile + (d * 32 + row) * StTile<ST>::PITCH + kk * 16);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.def[d].states) + ((tile_base + row) * rp + col) * sizeof(ST)) = val;
+                for (int i = 0; i < VPS; i++) {
+                    const int row = sr0 + (32 / VPS) * i;
+                    const uint32_t elem = cbase + (uint32_t)skv * (16 / SB);   // first row-element of this vector
+                    if (row < (int)rows_here && elem < Mpad) {
+                        const uint4 v = lds128(st_s + (d * 32 + row) * SPITCH + skv * 16);
+                        *reinterpret_cast<uint4*>(col + ((tile_base + row) * rp + elem) * SB) = v;
                     }
                 }
             }
+            // publish a word of granule flags every 32 granules and at the end of the rows
+            const uint32_t gcount = (chunk + 1) * (DCH / 16);
+            if ((gcount & 31u) == 0 || chunk + 1 == n_chunks) {
+                const uint32_t wi = (gcount - 1) >> 5;
+                if (valid && wi < p.fm_words) p.fmask[(size_t)wi * p.n_strings + idx] = fm;
+                fm = 0;
+            }
             __syncwarp();
         }
-
-        // per-tile counters: rows with enable = 0 all look up table row 0 (src/lib.rs:218-232 with enable = 0)
-        cta_counters_tile(cc, valid && !dead, M - L, (cold_store[CF_FLAGS] & B2R_ST_OVERLAP) != 0);
     }
 
-    __syncthreads();
-    cta_counters_flush<D>(p, ep_s, cc);
-
-    // ---- flush the multiplicity bins -----------------------------------------------------------------------------
-    if (HIST_SMEM) {
+    // ---- flush the multiplicity bins: bin (s,c) of def d -> dense global histogram [c*S + s] -------------------------------
+    if (HM == (int)HIST_SMEM) {
+        __syncthreads();
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            const uint32_t n = 256u * S_[d];
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t v = hist_t[d][i];
-                if (v) atomicAdd(p.def[d].hist + i, (unsigned long long)v);
+            const uint32_t S = p.def[d].num_states;
+            for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) {
+                const uint32_t s = i >> 8, c = i & 255u;
+                const uint32_t v = lds32(hist_s[d] + i * 4);
+                if (v) atomicAdd(p.def[d].hist + (size_t)c * S + s, (unsigned long long)v);
             }
         }
     }
 }
-
-template <int D, typename ST, bool TS, bool HS, int WARPS>
-static int launch_one(const WalkParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = walk_kernel<D, ST, TS, HS, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
-    kern<<<grid, WARPS * 32, smem, st>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("walk_kernel launch: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
-    return B2R_OK;
-}
-
-constexpr int WALK_WARPS = 8;
-
-// one instantiation set per number of defs (walk_inst.cu is compiled once per D, in parallel)
-template <int D>
-int launch_walk_d(const WalkParams& p, bool wide, bool ts, bool hs, size_t smem, int grid, cudaStream_t st);
 
 }  // namespace b2r

@@ -1,6 +1,7 @@
-// Instantiates walk_kernel for one number of regex defs (compiled once per D with -DB2R_INST_D=<D>, in parallel).
+// Instantiates walk_kernel and emit_kernel for one number of regex defs (compiled once per D with -DB2R_INST_D=<D>, in
+// parallel).
+#include "emit.cuh"
 #include "walk.cuh"
-#include "walk_direct.cuh"
 
 #ifndef B2R_INST_D
 #error "compile with -DB2R_INST_D=<1..4>"
@@ -8,39 +9,58 @@
 
 namespace b2r {
 
-template <>
-int launch_walk_d<B2R_INST_D>(const WalkParams& p, bool wide, bool ts, bool hs, size_t smem, int grid, cudaStream_t st) {
-    constexpr int D = B2R_INST_D;
-    if (wide) {
-        if (ts && hs) return launch_one<D, uint16_t, true, true, WALK_WARPS>(p, smem, grid, st);
-        if (ts) return launch_one<D, uint16_t, true, false, WALK_WARPS>(p, smem, grid, st);
-        return launch_one<D, uint16_t, false, false, WALK_WARPS>(p, smem, grid, st);
-    }
-    if (ts && hs) return launch_one<D, uint8_t, true, true, WALK_WARPS>(p, smem, grid, st);
-    if (ts) return launch_one<D, uint8_t, true, false, WALK_WARPS>(p, smem, grid, st);
-    return launch_one<D, uint8_t, false, false, WALK_WARPS>(p, smem, grid, st);
+template <int D, typename ST, int TM, int HM>
+static int launch_walk_one(const WalkParams& p, size_t smem, int grid, int block, cudaStream_t st) {
+    auto kern = walk_kernel<D, ST, TM, HM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(walk_kernel): %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
+    kern<<<grid, block, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("walk_kernel launch: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
+    return B2R_OK;
 }
 
 template <int D>
-int launch_direct_d(const WalkParams& p, const uint32_t* tab, bool in_row, size_t smem, int grid, int block, cudaStream_t st);
+int launch_walk_d(const WalkParams& p, bool wide, size_t smem, int grid, int block, cudaStream_t st);
 
-#if B2R_INST_D <= 2
-template <int D, bool HIST, bool IN_ROW>
-static int launch_direct_one(const WalkParams& p, const uint32_t* tab, size_t smem, int grid, int block, cudaStream_t st) {
-    auto kern = walk_direct_kernel<D, HIST, IN_ROW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
-    kern<<<grid, block, smem, st>>>(p, tab);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("walk_direct_kernel launch: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
+template <>
+int launch_walk_d<B2R_INST_D>(const WalkParams& p, bool wide, size_t smem, int grid, int block, cudaStream_t st) {
+    constexpr int D = B2R_INST_D;
+    const bool gtab = p.table_mode == TABLE_GLOBAL;
+    const bool shist = p.hist_mode == HIST_SMEM;
+    if (wide) {   // 2-byte states: more than 255 states, the bins never fit in shared memory
+        if (shist) { set_error("walk_kernel: shared-memory bins with 2-byte states"); return B2R_ERR_UNSUPPORTED; }
+        return gtab ? launch_walk_one<D, uint16_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st)
+                    : launch_walk_one<D, uint16_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+    }
+    if (gtab) {
+        if (shist) { set_error("walk_kernel: shared-memory bins with global tables"); return B2R_ERR_UNSUPPORTED; }
+        return launch_walk_one<D, uint8_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st);
+    }
+    return shist ? launch_walk_one<D, uint8_t, TABLE_REPL, HIST_SMEM>(p, smem, grid, block, st)
+                 : launch_walk_one<D, uint8_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+}
+
+template <int D>
+int launch_emit_d(const WalkParams& p, bool wide, size_t smem, int grid, cudaStream_t st);
+
+template <int D, typename ST>
+static int launch_emit_one(const WalkParams& p, size_t smem, int grid, cudaStream_t st) {
+    auto kern = emit_kernel<D, ST>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(emit_kernel): %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
+    }
+    kern<<<grid, EMIT_THREADS, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("emit_kernel launch: %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
     return B2R_OK;
 }
+
 template <>
-int launch_direct_d<B2R_INST_D>(const WalkParams& p, const uint32_t* tab, bool in_row, size_t smem, int grid, int block, cudaStream_t st) {
+int launch_emit_d<B2R_INST_D>(const WalkParams& p, bool wide, size_t smem, int grid, cudaStream_t st) {
     constexpr int D = B2R_INST_D;
-    if (!p.want_hist) return launch_direct_one<D, false, true>(p, tab, smem, grid, block, st);
-    return in_row ? launch_direct_one<D, true, true>(p, tab, smem, grid, block, st) : launch_direct_one<D, true, false>(p, tab, smem, grid, block, st);
+    return wide ? launch_emit_one<D, uint16_t>(p, smem, grid, st) : launch_emit_one<D, uint8_t>(p, smem, grid, st);
 }
-#endif
 
 }  // namespace b2r

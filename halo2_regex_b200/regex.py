@@ -263,6 +263,18 @@ class RegexVerifyConfig:
         _raise(lib.b2r_last_kernel_ms(self._h, C.byref(w), C.byref(t)))
         return w.value, t.value
 
+    def last_stage_ms(self):
+        """(walk_kernel, emit_kernel, finalize_kernel) device times of the last call, in ms."""
+        ms = (C.c_float * 3)()
+        _raise(lib.b2r_last_stage_ms(self._h, ms))
+        return ms[0], ms[1], ms[2]
+
+    def last_plan(self):
+        """(table placement, bin placement) chosen by the last call: see b2r_last_plan in include/b2r.h."""
+        t, h = C.c_uint32(), C.c_uint32()
+        _raise(lib.b2r_last_plan(self._h, C.byref(t), C.byref(h)))
+        return ("repl", "plain", "global")[t.value], ("none", "smem", "global")[h.value]
+
     # ---- match_substrs (src/lib.rs:311-773): one string ------------------------------------------------------------
     def match_substrs(self, characters, ctx=None):
         characters = bytes(characters)

@@ -231,6 +231,11 @@ uint32_t b2r_last_launch_count(const b2r_config*);
  * valid after b2r_batch_result().  Enabled by b2r_config_set_timing(cfg,1). */
 int b2r_config_set_timing(b2r_config*, int enable);
 int b2r_last_kernel_ms(b2r_config*, float* walk_ms, float* total_ms);
+/* device time (ms) of the three stages of the last call: ms3[0] walk_kernel, ms3[1] emit_kernel, ms3[2] finalize_kernel */
+int b2r_last_stage_ms(b2r_config*, float* ms3);
+/* where the last call kept the walk tables (0 replicated shared memory, 1 shared memory, 2 global) and the
+ * multiplicity bins (1 shared memory, 2 global) */
+int b2r_last_plan(const b2r_config*, uint32_t* table_mode, uint32_t* hist_mode);
 
 #ifdef __cplusplus
 }

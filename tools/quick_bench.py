@@ -37,6 +37,7 @@ algo = N * L + out.written_bytes()
 for it in range(args.iters):
     cfg.match_batch_device(d_bytes, d_offs, out)
     res = cfg.batch_result()
-    w, t = cfg.last_kernel_ms()
-    print(f"iter {it}: walk {w:.3f} ms total {t:.3f} ms -> input {N * L / w / 1e6:.1f} GB/s, algorithmic {algo / w / 1e6:.1f} GB/s "
-          f"({algo / w / 1e6 / 6555.2 * 100:.1f}% of measured HBM peak), code {res.code}")
+    w, e, f = cfg.last_stage_ms()
+    t = w + e + f
+    print(f"iter {it}: walk {w:.3f} + emit {e:.3f} + finalize {f:.3f} = {t:.3f} ms -> input {N * L / t / 1e6:.1f} GB/s, algorithmic {algo / t / 1e6:.1f} GB/s "
+          f"({algo / t / 1e6 / 6555.2 * 100:.1f}% of measured HBM peak), plan {cfg.last_plan()}, code {res.code}")
