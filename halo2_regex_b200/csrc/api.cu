@@ -178,6 +178,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
+    { const char* dbg = getenv("B2R_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
     p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;

@@ -1,22 +1,24 @@
 // emit_kernel — stage 2 of the batch path: everything the reference derives from the state sequence.
 //
-// One WARP per string.  Inputs: the string, its state columns and its granule flags (walk.cuh).  Outputs, written as whole
-// rows (zeros and values merged before the store, so DRAM sees exactly the algorithmic bytes):
+// One WARP per tile of 32 consecutive strings.  Inputs: the strings, their state columns and granule flags (walk.cuh).
+// Outputs (every row is written within microseconds by one warp, so zeros and values merge in L2 and DRAM sees the
+// algorithmic bytes once):
 //   per-def substr ids (src/lib.rs:825-845), start_enable / end_enable bitmaps (:482-513), the endpoint-lookup
 //   multiplicities (:235-284), masked_chars / masked_substr_ids (:740-764), substring records + compact bytes, the
 //   accept flag (:427-457) and the status record.
 //
-// Step 1: every 16-byte vector of every column whose granule is NOT flagged is zero (a row with a non-zero value has a
-//         non-zero substr id in some def, and start/end flags require one): coalesced 16-byte zero stores.
-// Step 2: flagged 32-row windows, in order, lane = row: the row's packed entries are looked up again from
-//         (byte, state) — one lookup replaces the reference's HashSet probes and `contains` scans — and give substr id,
-//         is_start, is_end(next row).  Ballots turn them into bitmap words; shuffles give the neighbour rows.
+// Phase A (lane = string): offsets, granule flags, final states of the tile's 32 strings (coalesced).
+// Phase B: the tile's rows of every sparse column are contiguous in memory: blanket zero-fill with 16-byte stores.
+// Phase C (lane = string): every lane scans the flagged granules of ITS string, in order.  A row's packed entries are
+//         looked up again from (byte, state) — one lookup replaces the reference's HashSet probes and `contains` scans —
+//         and give substr id, is_start, is_end(next row).  Non-zero values overwrite the zeros of phase B in L2.
+// Phase D (lane = string): accept flags and status records.
 // Masks.  With b_1 < b_2 < ... the rows where the id sum changes AND is_start_sum|is_end_sum is set, the forward scan
 //         (src/lib.rs:598-645) sets start_mask at b_k when is_start_sum[b_k] and resets it when only is_end_sum[b_k]; the
 //         backward scan (:663-714) sets end_mask for the rows before b_{k+1} when is_end_sum[b_{k+1}] and resets it when
 //         only is_start_sum[b_{k+1}].  Hence mask = 1 exactly on [b_k, b_{k+1}) with is_start at b_k and is_end at b_{k+1}.
-//         The boundaries are streamed in order; a closing boundary makes the warp overwrite the masked rows of
-//         [b_k, b_{k+1}) (they may extend over unflagged granules) — same L2 lines it has just zeroed.
+//         The boundaries are streamed in order; a closing boundary makes the lane overwrite the masked rows of
+//         [b_k, b_{k+1}) (they may extend over unflagged granules) — same L2 lines the warp has just zeroed.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -84,86 +86,69 @@ struct EmitTotals {
 };
 
 // rows [a,b) of string j are masked: start_mask = end_mask = 1 (src/lib.rs:740-764), b <= len.  Writes masked_chars,
-// masked_substr_ids, the compact bytes and one record per maximal run of a constant id sum.  Warp-cooperative; every
-// argument is warp-uniform.  Returns the updated (n_rec, n_cmp).
+// masked_substr_ids, the compact bytes and one record per maximal run of a constant id sum.  Lane-private (one thread,
+// its own string).  Returns the updated (n_rec, n_cmp).
 template <int D, typename ST>
 static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const EmitTables<D> tb, uint64_t j, const uint8_t* src, uint32_t a, uint32_t b,
                                                   uint32_t n_rec, uint32_t n_cmp) {
-    const int lane = threadIdx.x & 31;
     uint8_t* const mc = p.masked_chars ? p.masked_chars + j * p.row_pitch : nullptr;
     uint8_t* const ms = p.masked_substr_ids ? p.masked_substr_ids + j * p.row_pitch : nullptr;
     uint8_t* const cb = p.compact_bytes ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
     auto record = [&](uint32_t start, uint32_t len, uint32_t sid, uint32_t coff) {
-        if (lane == 0 && p.records && n_rec < p.max_records) {
+        if (p.records && n_rec < p.max_records) {
             b2r_substr_record r; r.start = start; r.len = len; r.substr_id = sid; r.compact_off = coff;
             p.records[j * p.max_records + n_rec] = r;
         }
         n_rec++;
     };
-    uint32_t run_start = a, run_sum = 0, last_sum = 0;
-    for (uint32_t base = a; base < b; base += 32) {
-        const uint32_t i = base + lane;
-        const bool in = i < b;
-        uint32_t c = 0, sum = 0;
-        if (in) {
-            c = src[i];
+    uint32_t run_start = a, run_sum = 0;
+    for (uint32_t i = a; i < b; i++) {
+        const uint32_t c = src[i];
+        uint32_t sum = 0;
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                const uint32_t S = p.def[d].num_states;
-                const uint32_t s = (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[j * p.row_pitch + i];
-                if (s < S) sum += ent_sid(tb.trans[d][(uint32_t)tb.cls[d][c] * S + s]);
-            }
-            if (mc) mc[i] = (uint8_t)c;
-            if (ms) ms[i] = (uint8_t)sum;
-            const uint32_t k = n_cmp + (i - a);
-            if (cb && k < p.compact_pitch) cb[k] = (uint8_t)c;
+        for (int d = 0; d < D; d++) {
+            const uint32_t S = p.def[d].num_states;
+            const uint32_t s = (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[j * p.row_pitch + i];
+            if (s < S) sum += ent_sid(tb.trans[d][(uint32_t)tb.cls[d][c] * S + s]);
         }
-        // records: maximal runs of a constant id sum
-        uint32_t before = __shfl_up_sync(0xffffffffu, sum, 1);
-        if (lane == 0) before = last_sum;
-        const bool starts = in && (i == a || sum != before);
-        uint32_t sm = __ballot_sync(0xffffffffu, starts);
-        while (sm) {
-            const int l = __ffs((int)sm) - 1;
-            sm &= sm - 1;
-            const uint32_t pos = base + l;
-            const uint32_t s_here = __shfl_sync(0xffffffffu, sum, l);
-            if (pos != a) record(run_start, pos - run_start, run_sum, n_cmp + (run_start - a));
-            run_start = pos; run_sum = s_here;
+        if (mc && !(p.debug & 16)) mc[i] = (uint8_t)c;
+        if (ms && sum && !(p.debug & 16)) ms[i] = (uint8_t)sum;
+        const uint32_t k = n_cmp + (i - a);
+        if (cb && k < p.compact_pitch) cb[k] = (uint8_t)c;
+        if (i == a) run_sum = sum;
+        else if (sum != run_sum) {                                       // records: maximal runs of a constant id sum
+            record(run_start, i - run_start, run_sum, n_cmp + (run_start - a));
+            run_start = i; run_sum = sum;
         }
-        last_sum = __shfl_sync(0xffffffffu, sum, 31);
     }
     record(run_start, b - run_start, run_sum, n_cmp + (run_start - a));
     return make_uint2(n_rec, n_cmp + (b - a));
 }
 
+// Lane-private scan of ONE string's flagged granules, in order (phase C).  Streams the boundaries of the mask algebra.
 template <int D, typename ST>
-struct StringEmitter {
+struct LaneScan {
     const WalkParams& p;
     const EmitTables<D>& tb;
-    const int lane;
-    // the string
     uint64_t j;
     const uint8_t* src;
     uint32_t L;
-    // streaming state (warp-uniform)
     bool prev_valid, prev_is;   // last boundary: is_start_sum set there
     uint32_t prev_pos;
-    bool carry_valid;           // rows up to carry_pos-1 have been examined; carry_s / carry_ie belong to row carry_pos-1
-    uint32_t carry_pos, carry_s, carry_ie;
+    uint32_t next_row;          // last examined row + 1; NO_POS = none yet / gap closed
+    uint32_t carry_s, carry_ie; // id sum of row next_row-1, is_end_sum[next_row] (0 after a gap)
     uint32_t n_rec, n_cmp;
-    bool overlap;
+    bool overlap, invalid;
+    uint32_t bw_t, sw[D], ew[D];   // bitmap words being assembled: rows [32*bw_t, 32*bw_t+32)
 
-    __device__ __forceinline__ StringEmitter(const WalkParams& p_, const EmitTables<D>& tb_, int lane_) : p(p_), tb(tb_), lane(lane_) {}
-
-    __device__ __forceinline__ uint32_t state_at(int d, uint32_t row) const {
-        return (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[j * p.row_pitch + row];
-    }
-    // packed entry of row `row` (< L): the transition taken from state s on byte c
-    __device__ __forceinline__ uint32_t entry(int d, uint32_t c, uint32_t s) const {
-        const uint32_t S = p.def[d].num_states;
-        if (s >= S) return ENT_INVALID;                                  // the walk parked this def in the trap state
-        return tb.trans[d][(uint32_t)tb.cls[d][c] * S + s];
+    __device__ __forceinline__ LaneScan(const WalkParams& p_, const EmitTables<D>& tb_, uint64_t j_, const uint8_t* src_, uint32_t L_)
+        : p(p_), tb(tb_), j(j_), src(src_), L(L_) {
+        prev_valid = false; prev_is = false; prev_pos = 0;
+        next_row = NO_POS; carry_s = 0; carry_ie = 0;
+        n_rec = 0; n_cmp = 0; overlap = false; invalid = false;
+        bw_t = NO_POS;
+#pragma unroll
+        for (int d = 0; d < D; d++) { sw[d] = 0; ew[d] = 0; }
     }
 
     // a row where the id sum changes and is_start_sum | is_end_sum is set
@@ -174,173 +159,225 @@ struct StringEmitter {
         }
         prev_valid = true; prev_pos = pos; prev_is = b_is;
     }
-
-    // the rows after carry_pos-1 are not examined (their granule is not flagged: id sum 0, no is_start); row carry_pos can
-    // still be a boundary: the id sum drops to 0 there and is_end_sum[carry_pos] comes from row carry_pos-1
+    // the rows from next_row on are not examined (their granule is not flagged: id sum 0, no is_start) or lie past the end
+    // of the string; row next_row can still be a boundary: the id sum drops to 0 there and is_end_sum[next_row] comes from
+    // the row before
     __device__ __forceinline__ void close_gap() {
-        if (carry_valid && carry_s != 0 && carry_ie != 0) {
+        if (next_row != NO_POS && carry_s != 0 && carry_ie != 0) {
             if (carry_ie > 1) overlap = true;
-            boundary(carry_pos, false, true);
+            boundary(next_row, false, true);
         }
-        carry_valid = false; carry_s = 0; carry_ie = 0;
+        next_row = NO_POS; carry_s = 0; carry_ie = 0;
     }
-
-    // rows [32t, 32t+32); halves: bit h set = granule 2t+h is flagged (only those bytes are written here).  Returns false
-    // when the string hit an invalid transition.
-    __device__ __forceinline__ bool window(uint32_t t, uint32_t halves) {
-        const uint32_t i = 32 * t + lane;
-        if (carry_valid && carry_pos != 32 * t) close_gap();
-        const bool is_char = i < L;
-        uint32_t c = 0;
-        if (is_char) c = src[i];
-        uint32_t sum = 0, is_sum = 0, ie_next = 0, inval = 0;
-        uint32_t e[D], s[D];
+    __device__ __forceinline__ void flush_bitmap_words() {
+        if (bw_t == NO_POS || (p.debug & 16)) return;
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            e[d] = 0; s[d] = 0;
-            if (is_char) {
-                s[d] = state_at(d, i);
-                e[d] = entry(d, c, s[d]);
-                inval |= e[d] & ENT_INVALID;
-                sum += ent_sid(e[d]);
-                is_sum += (e[d] >> 24) & 1u;
-                ie_next += (e[d] >> 25) & 1u;
-            }
+            if (sw[d] && p.def[d].start_enable) *reinterpret_cast<uint32_t*>(p.def[d].start_enable + j * p.bitmap_pitch + 4 * bw_t) = sw[d];
+            if (ew[d] && p.def[d].end_enable) *reinterpret_cast<uint32_t*>(p.def[d].end_enable + j * p.bitmap_pitch + 4 * bw_t) = ew[d];
+            sw[d] = 0; ew[d] = 0;
         }
-        if (__any_sync(0xffffffffu, inval != 0)) return false;
-        uint32_t sum_before = __shfl_up_sync(0xffffffffu, sum, 1);
-        uint32_t ie_here = __shfl_up_sync(0xffffffffu, ie_next, 1);
-        if (lane == 0) { sum_before = carry_s; ie_here = carry_ie; }     // zero unless the previous window was examined too
-        const bool bnd = (sum != sum_before) && (is_sum | ie_here);
-        if (__any_sync(0xffffffffu, is_sum > 1 || ie_here > 1)) overlap = true;
-
-        // ---- per-def columns --------------------------------------------------------------------------------------
-        const bool mine = (halves >> (lane >> 4)) & 1u;                  // my half of the window is flagged (else zero-filled in step 1)
+    }
+    // row i < L with byte c and states s[].  Rows with an id sum of 0 in every def may be skipped by the caller: they are
+    // treated like the rows of an unflagged granule.
+    __device__ __forceinline__ void row(uint32_t i, uint32_t c, const uint32_t* s) {
+        if (next_row != i) close_gap();
+        uint32_t sum = 0, is_sum = 0, ie_next = 0;
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t S = p.def[d].num_states;
-            const uint32_t sid = ent_sid(e[d]);
-            if (mine && p.def[d].substr_ids && i < p.max_chars) p.def[d].substr_ids[j * p.row_pitch + i] = (uint8_t)sid;
-            const bool st = (e[d] & ENT_IS_START) != 0, en = (e[d] & ENT_IS_END) != 0;
-            const uint32_t sw = __ballot_sync(0xffffffffu, st), ew = __ballot_sync(0xffffffffu, en);
-            if (lane == 0) {                                             // the whole bitmap word belongs to this window
-                if (p.def[d].start_enable) *reinterpret_cast<uint32_t*>(p.def[d].start_enable + j * p.bitmap_pitch + 4 * t) = sw;
-                if (p.def[d].end_enable) *reinterpret_cast<uint32_t*>(p.def[d].end_enable + j * p.bitmap_pitch + 4 * t) = ew;
-            }
-            if (st) {                                                    // endpoint lookup, src/lib.rs:235-258
+            const uint32_t e = s[d] < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + s[d]] : ENT_INVALID;   // trap state: the walk parked this def
+            if (e & ENT_INVALID) { invalid = true; continue; }
+            const uint32_t sid = ent_sid(e);
+            if (!sid) continue;
+            sum += sid;
+            if (p.def[d].substr_ids && !(p.debug & 16)) p.def[d].substr_ids[j * p.row_pitch + i] = (uint8_t)sid;
+            if (e & ENT_IS_START) {                                      // start_enable, endpoint lookup src/lib.rs:235-258
+                is_sum++;
+                sw[d] |= 1u << (i & 31);
                 const uint32_t bin = (sid - p.def[d].sid_offset) * S + s[d];
                 if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + bin, 1u); else atomicAdd(p.def[d].ep_start + bin, 1ull);
             }
-            if (en) {                                                    // src/lib.rs:260-284
-                const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e[d] & ENT_NEXT_MASK);
+            if (e & ENT_IS_END) {                                        // end_enable, endpoint lookup src/lib.rs:260-284
+                ie_next++;
+                ew[d] |= 1u << (i & 31);
+                const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e & ENT_NEXT_MASK);
                 if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + p.def[d].num_substrs * S + bin, 1u); else atomicAdd(p.def[d].ep_end + bin, 1ull);
             }
         }
-        if (mine && i < p.max_chars) {                                   // masked rows are overwritten when their segment closes
-            if (p.masked_chars) p.masked_chars[j * p.row_pitch + i] = 0;
-            if (p.masked_substr_ids) p.masked_substr_ids[j * p.row_pitch + i] = 0;
-        }
-        __syncwarp();
-
-        // ---- boundaries, in order ----------------------------------------------------------------------------------
-        uint32_t bm = __ballot_sync(0xffffffffu, bnd);
-        const uint32_t ism = __ballot_sync(0xffffffffu, is_sum != 0), iem = __ballot_sync(0xffffffffu, ie_here != 0);
-        while (bm) {
-            const int l = __ffs((int)bm) - 1;
-            bm &= bm - 1;
-            boundary(32 * t + l, (ism >> l) & 1u, (iem >> l) & 1u);
-        }
-        carry_valid = true; carry_pos = 32 * t + 32;
-        carry_s = __shfl_sync(0xffffffffu, sum, 31);
-        carry_ie = __shfl_sync(0xffffffffu, ie_next, 31);
-        return true;
+        if (is_sum > 1 || carry_ie > 1) overlap = true;
+        if (sum != carry_s && (is_sum | carry_ie)) boundary(i, is_sum != 0, carry_ie != 0);
+        carry_s = sum; carry_ie = ie_next; next_row = i + 1;
     }
+    // granule g: rows [16g, 16g+16)
+    __device__ __forceinline__ void granule(uint32_t g) {
+        const uint32_t base = 16 * g;
+        if ((g >> 1) != bw_t) { flush_bitmap_words(); bw_t = g >> 1; }
+        // 16 bytes of the string from an arbitrary address: two aligned 16-byte loads, shifted into place.  The second
+        // one is only touched when the bytes needed reach into it.
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src + base);
+        const uint32_t sh = (uint32_t)(addr & 15);
+        const uint32_t n = L - base < 16 ? L - base : 16;              // rows of this granule that are characters (>= 1)
+        const uint4* q = reinterpret_cast<const uint4*>(addr - sh);
+        const uint4 v0 = __ldg(q);
+        uint4 v1 = make_uint4(0, 0, 0, 0);
+        if (sh + n > 16) v1 = __ldg(q + 1);
+        uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t y[7], z[5], w[4];
+#pragma unroll
+        for (int k = 0; k < 7; k++) y[k] = (sh & 4) ? x[k + 1] : x[k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) z[k] = (sh & 8) ? y[k + 2] : y[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = __funnelshift_r(z[k], z[k + 1], (sh & 3) * 8);
+        uint32_t sv[D][4 * sizeof(ST)];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const ST*>(p.def[d].states) + j * p.row_pitch + base);
+            const uint4 a = __ldg(sp);
+            sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
+            if (sizeof(ST) == 2) { const uint4 b2 = __ldg(sp + 1); sv[d][4] = b2.x; sv[d][5] = b2.y; sv[d][6] = b2.z; sv[d][7] = b2.w; }
+        }
+        // pass 1, unrolled, all lanes in step: which rows carry a substr id (or an invalid transition)?
+        uint32_t hot = 0;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const uint32_t c = (w[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const uint32_t S = p.def[d].num_states;
+                const uint32_t st = sizeof(ST) == 1 ? (sv[d][r >> 2] >> (8 * (r & 3))) & 0xFFu : (sv[d][r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+                const uint32_t e = st < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + st] : ENT_INVALID;
+                if (e & (ENT_SID_MASK | ENT_INVALID)) hot |= 1u << r;
+            }
+        }
+        hot &= (1u << n) - 1u;                                           // rows past the end of the string are not characters
+        // pass 2, one loop body shared by all lanes: each lane handles ITS next hot row
+        while (hot) {
+            const uint32_t r = (uint32_t)__ffs((int)hot) - 1u;
+            hot &= hot - 1;
+            const uint32_t wq = r < 8 ? (r < 4 ? w[0] : w[1]) : (r < 12 ? w[2] : w[3]);
+            const uint32_t c = (wq >> (8 * (r & 3))) & 0xFFu;
+            uint32_t st[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                if (sizeof(ST) == 1) {
+                    const uint32_t q = r < 8 ? (r < 4 ? sv[d][0] : sv[d][1]) : (r < 12 ? sv[d][2] : sv[d][3]);
+                    st[d] = (q >> (8 * (r & 3))) & 0xFFu;
+                } else {
+                    const uint32_t lo = r < 4 ? (r < 2 ? sv[d][0] : sv[d][1]) : (r < 6 ? sv[d][2] : sv[d][3]);
+                    const uint32_t hi = r < 12 ? (r < 10 ? sv[d][4 * (sizeof(ST) - 1)] : sv[d][4 * (sizeof(ST) - 1) + 1]) : (r < 14 ? sv[d][4 * (sizeof(ST) - 1) + 2] : sv[d][4 * (sizeof(ST) - 1) + 3]);
+                    st[d] = ((r < 8 ? lo : hi) >> (16 * (r & 1))) & 0xFFFFu;
+                }
+            }
+            row(base + r, c, st);
+        }
+    }
+    __device__ __forceinline__ void finish() { close_gap(); flush_bitmap_words(); }
+};
 
-    __device__ __forceinline__ void run(uint64_t j_, EmitTotals& tot) {
-        j = j_;
+// Warp-cooperative emitter for one tile of 32 consecutive strings.
+template <int D, typename ST>
+struct TileEmitter {
+    const WalkParams& p;
+    const EmitTables<D>& tb;
+    const int lane;
+
+    __device__ __forceinline__ TileEmitter(const WalkParams& p_, const EmitTables<D>& tb_, int lane_) : p(p_), tb(tb_), lane(lane_) {}
+
+    // One tile.  Phase A (lane = string): offsets, granule flags, final states.  Phase B: the tile's rows of every sparse
+    // column are contiguous — blanket zero-fill with 16-byte stores.  Phase C (lane = string): every lane scans the flagged
+    // granules of its own string.  Phase D (lane = string): accept rule (src/lib.rs:427-457) and the status records.
+    __device__ __forceinline__ void run_tile(uint64_t tile, EmitTotals& tot) {
         const uint64_t N = p.n_strings;
         const uint32_t M = p.max_chars;
-        const uint64_t off = p.offsets[j], end = p.offsets[j + 1];
-        if (end < off || end - off > (uint64_t)(M - 1)) {                // len must be <= M-1
-            if (lane == 0) kill_string(p, j);
-            return;
-        }
-        src = p.bytes + off;
-        L = (uint32_t)(end - off);
         const uint64_t rp = p.row_pitch, bp = p.bitmap_pitch;
+        const uint64_t tile_base = tile * 32;
+        const uint64_t jl = tile_base + lane;
+        const bool valid = jl < N;
+        const uint64_t rows_here = N - tile_base < 32 ? N - tile_base : 32;
 
-        // ---- step 1: zero every vector whose granule is not flagged -------------------------------------------------
-        const uint32_t nvec = (M + 15) / 16;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (uint32_t k = 0; k * 32 < nvec; k++) {
-            const uint32_t v = k * 32 + lane;
-            const uint32_t fw = k < p.fm_words ? __ldg(p.fmask + (size_t)k * N + j) : 0u;
-            if (v < nvec && !((fw >> lane) & 1u)) {
-                const uint64_t o = j * rp + 16ull * v;
+        // ---- A ----------------------------------------------------------------------------------------------------
+        uint64_t off = 0, end = 0;
+        if (valid) { off = p.offsets[jl]; end = p.offsets[jl + 1]; }
+        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // len must be <= M-1
+        const bool live = valid && !too_long;
+        const uint32_t Ll = live ? (uint32_t)(end - off) : 0u;
+        uint32_t fw0 = 0, fw1 = 0;
+        if (live && p.fm_words > 0) fw0 = __ldg(p.fmask + jl);
+        if (live && p.fm_words > 1) fw1 = __ldg(p.fmask + N + jl);
+        uint32_t fin[D];
 #pragma unroll
-                for (int d = 0; d < D; d++)
-                    if (p.def[d].substr_ids) *reinterpret_cast<uint4*>(p.def[d].substr_ids + o) = z;
-                if (p.masked_chars) *reinterpret_cast<uint4*>(p.masked_chars + o) = z;
-                if (p.masked_substr_ids) *reinterpret_cast<uint4*>(p.masked_substr_ids + o) = z;
+        for (int d = 0; d < D; d++) fin[d] = (live && !(p.debug & 4)) ? (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[jl * rp + Ll] : 0xFFFFFFFEu;
+
+        // ---- B ----------------------------------------------------------------------------------------------------
+        auto zero_region = [&](uint8_t* base, uint64_t bytes) {   // base 16-byte aligned, bytes a multiple of 4
+            if (!base || (p.debug & 1)) return;
+            const uint64_t nv = bytes / 16;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint64_t v = lane; v < nv; v += 32) reinterpret_cast<uint4*>(base)[v] = z;
+            for (uint64_t o = nv * 16 + (uint64_t)lane * 4; o < bytes; o += 128) *reinterpret_cast<uint32_t*>(base + o) = 0u;
+        };
+        auto phase_b = [&]() {
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            zero_region(p.def[d].substr_ids ? p.def[d].substr_ids + tile_base * rp : nullptr, rows_here * rp);
+            zero_region(p.def[d].start_enable ? p.def[d].start_enable + tile_base * bp : nullptr, rows_here * bp);
+            zero_region(p.def[d].end_enable ? p.def[d].end_enable + tile_base * bp : nullptr, rows_here * bp);
+        }
+        zero_region(p.masked_chars ? p.masked_chars + tile_base * rp : nullptr, rows_here * rp);
+        zero_region(p.masked_substr_ids ? p.masked_substr_ids + tile_base * rp : nullptr, rows_here * rp);
+            __syncwarp();                                                // the zeros are ordered before the values of phase C
+        };
+        if (!(p.debug & 32)) phase_b();
+
+        // ---- C ----------------------------------------------------------------------------------------------------
+        uint32_t r_nrec = 0, r_ncmp = 0, r_flags = 0;
+        if (live && !(p.debug & 2) && (p.fm_words > 2 || (fw0 | fw1) != 0)) {
+            LaneScan<D, ST> sc(p, tb, jl, p.bytes + off, Ll);
+            for (uint32_t w = 0; w < p.fm_words && !sc.invalid; w++) {
+                uint32_t bits = w == 0 ? fw0 : w == 1 ? fw1 : __ldg(p.fmask + (size_t)w * N + jl);
+                while (bits && !sc.invalid) {
+                    const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
+                    bits &= bits - 1;
+                    sc.granule(w * 32 + g);
+                }
+            }
+            if (sc.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
+            else {
+                sc.finish();
+                r_nrec = sc.n_rec; r_ncmp = sc.n_cmp;
+                if (sc.overlap) r_flags = B2R_ST_OVERLAP;
             }
         }
-        const uint32_t nbw = (M + 31) / 32;                              // bitmap words: word t = rows [32t, 32t+32) = granules 2t, 2t+1
-        for (uint32_t k = 0; k * 32 < nbw; k++) {
-            const uint32_t t = k * 32 + lane;
-            const uint32_t wi = (2 * t) >> 5;
-            const uint32_t fw = (t < nbw && wi < p.fm_words) ? __ldg(p.fmask + (size_t)wi * N + j) : 0u;
-            if (t < nbw && !((fw >> ((2 * t) & 31)) & 3u)) {
+
+        if (p.debug & 32) phase_b();
+        // ---- D ----------------------------------------------------------------------------------------------------
+        if (valid && !(p.debug & 8)) {
+            if (too_long || (r_flags & B2R_ST_INVALID_TRANSITION)) kill_string(p, jl);
+            else {
+                uint32_t flags = r_flags;
 #pragma unroll
-                for (int d = 0; d < D; d++) {
-                    if (p.def[d].start_enable) *reinterpret_cast<uint32_t*>(p.def[d].start_enable + j * bp + 4 * t) = 0u;
-                    if (p.def[d].end_enable) *reinterpret_cast<uint32_t*>(p.def[d].end_enable + j * bp + 4 * t) = 0u;
+                for (int d = 0; d < D; d++)
+                    if (fin[d] == p.def[d].accepted_state) flags |= B2R_ST_ACCEPTED(d);
+                if (p.records && r_nrec > p.max_records) flags |= B2R_ST_RECORDS_TRUNCATED;
+                if (p.compact_bytes && r_ncmp > p.compact_pitch) flags |= B2R_ST_COMPACT_TRUNCATED;
+                if (p.status) {
+                    b2r_string_status st = {};
+                    st.flags = flags; st.err_pos = NO_POS; st.n_records = r_nrec; st.n_compact = r_ncmp;
+                    p.status[jl] = st;
                 }
+                tot.pad_rows += M - Ll; tot.n_ok++; tot.n_overlap += (r_flags & B2R_ST_OVERLAP) ? 1u : 0u;
             }
         }
         __syncwarp();
-
-        // ---- step 2: flagged windows, in order ----------------------------------------------------------------------
-        prev_valid = false; prev_is = false; prev_pos = 0;
-        carry_valid = false; carry_pos = 0; carry_s = 0; carry_ie = 0;
-        n_rec = 0; n_cmp = 0; overlap = false;
-        for (uint32_t w = 0; w < p.fm_words; w++) {
-            uint32_t bits = __ldg(p.fmask + (size_t)w * N + j);
-            while (bits) {
-                const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
-                const uint32_t lo = g & ~1u;
-                const uint32_t halves = (bits >> lo) & 3u;
-                bits &= ~(3u << lo);
-                if (!window((w * 32 + g) >> 1, halves)) {
-                    if (lane == 0) kill_string(p, j);
-                    return;
-                }
-            }
-        }
-        close_gap();
-
-        // ---- accept rule (src/lib.rs:427-457) and the status record ----------------------------------------------------
-        uint32_t flags = 0;
-#pragma unroll
-        for (int d = 0; d < D; d++)
-            if (state_at(d, L) == p.def[d].accepted_state) flags |= B2R_ST_ACCEPTED(d);
-        if (overlap) flags |= B2R_ST_OVERLAP;
-        if (p.records && n_rec > p.max_records) flags |= B2R_ST_RECORDS_TRUNCATED;
-        if (p.compact_bytes && n_cmp > p.compact_pitch) flags |= B2R_ST_COMPACT_TRUNCATED;
-        if (p.status && lane == 0) {
-            b2r_string_status st = {};
-            st.flags = flags; st.err_pos = NO_POS; st.n_records = n_rec; st.n_compact = n_cmp;
-            p.status[j] = st;
-        }
-        tot.pad_rows += M - L; tot.n_ok++; tot.n_overlap += overlap ? 1u : 0u;
     }
 };
 
-template <int D, typename ST>
-__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ WalkParams p) {
-    extern __shared__ __align__(16) unsigned char esmem[];
-    const int lane = threadIdx.x & 31;
-    EmitTables<D> tb;
-    // shared memory: endpoint counters, then (optionally) the lookup tables
+// shared memory of the emitter: endpoint counters, then (optionally) the lookup tables.  Every thread of the CTA calls
+// this, followed by a __syncthreads().
+template <int D>
+__device__ __forceinline__ void emit_tables_init(const WalkParams& p, unsigned char* esmem, EmitTables<D>& tb) {
     uint32_t off = 0;
 #pragma unroll
     for (int d = 0; d < D; d++) {
@@ -364,18 +401,19 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
             tb.trans[d] = p.def[d].trans; tb.cls[d] = p.def[d].byte_class;
         }
     }
-    __syncthreads();
+}
 
-    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    StringEmitter<D, ST> em(p, tb, lane);
-    EmitTotals tot;
-    for (uint64_t j = gw; j < p.n_strings; j += warps_total) em.run(j, tot);
-
-    if (lane == 0) {
-        if (tot.pad_rows) atomicAdd(&p.counters->pad_rows, tot.pad_rows);
-        if (tot.n_overlap) atomicAdd(&p.counters->n_overlap, (unsigned long long)tot.n_overlap);
-        if (tot.n_ok) atomicAdd(&p.counters->n_ok_strings, (unsigned long long)tot.n_ok);
+// publish the per-lane totals and the CTA's endpoint counters; every thread of the CTA calls this
+template <int D>
+__device__ __forceinline__ void emit_publish(const WalkParams& p, const EmitTables<D>& tb, const EmitTotals& tot) {
+    unsigned long long psum = tot.pad_rows;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+    const uint32_t nok = __reduce_add_sync(0xffffffffu, tot.n_ok), nov = __reduce_add_sync(0xffffffffu, tot.n_overlap);
+    if ((threadIdx.x & 31) == 0) {
+        if (psum) atomicAdd(&p.counters->pad_rows, psum);
+        if (nov) atomicAdd(&p.counters->n_overlap, (unsigned long long)nov);
+        if (nok) atomicAdd(&p.counters->n_ok_strings, (unsigned long long)nok);
     }
     __syncthreads();
 #pragma unroll
@@ -387,6 +425,22 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
             if (v) atomicAdd((i < ks ? p.def[d].ep_start + i : p.def[d].ep_end + (i - ks)), (unsigned long long)v);
         }
     }
+}
+
+template <int D, typename ST>
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ WalkParams p) {
+    extern __shared__ __align__(16) unsigned char esmem[];
+    const int lane = threadIdx.x & 31;
+    EmitTables<D> tb;
+    emit_tables_init<D>(p, esmem, tb);
+    __syncthreads();
+
+    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    TileEmitter<D, ST> em(p, tb, lane);
+    EmitTotals tot;
+    for (uint64_t tile = gw; tile < p.n_tiles; tile += warps_total) em.run_tile(tile, tot);
+    emit_publish<D>(p, tb, tot);
 }
 
 }  // namespace b2r

@@ -41,3 +41,15 @@ for it in range(args.iters):
     t = w + e + f
     print(f"iter {it}: walk {w:.3f} + emit {e:.3f} + finalize {f:.3f} = {t:.3f} ms -> input {N * L / t / 1e6:.1f} GB/s, algorithmic {algo / t / 1e6:.1f} GB/s "
           f"({algo / t / 1e6 / 6555.2 * 100:.1f}% of measured HBM peak), plan {cfg.last_plan()}, code {res.code}")
+
+# pure-write reference: zero every sparse column with torch (cudaMemset path)
+cols = [t for t in [out.masked_chars, out.masked_substr_ids] + list(out.substr_ids) + list(out.start_enable) + list(out.end_enable) if t is not None]
+nbytes = sum(t.numel() * t.element_size() for t in cols)
+for it in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in cols:
+        t.zero_()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"memset of the sparse columns: {nbytes / 1e9:.2f} GB in {ms:.3f} ms = {nbytes / ms / 1e6:.0f} GB/s")
