@@ -1,24 +1,24 @@
-// emit_kernel — stage 2 of the batch path: everything the reference derives from the state sequence.
+// Emit stage: everything the reference derives from the state sequence, for one tile of 32 consecutive strings per warp.
 //
-// One WARP per tile of 32 consecutive strings.  Inputs: the strings, their state columns and granule flags (walk.cuh).
-// Outputs (every row is written within microseconds by one warp, so zeros and values merge in L2 and DRAM sees the
-// algorithmic bytes once):
-//   per-def substr ids (src/lib.rs:825-845), start_enable / end_enable bitmaps (:482-513), the endpoint-lookup
-//   multiplicities (:235-284), masked_chars / masked_substr_ids (:740-764), substring records + compact bytes, the
-//   accept flag (:427-457) and the status record.
+// Inputs: the strings, their state columns and granule flags (walk.cuh).  Outputs: per-def substr ids (src/lib.rs:825-845),
+// start_enable / end_enable bitmaps (:482-513), the endpoint-lookup multiplicities (:235-284), masked_chars /
+// masked_substr_ids (:740-764), substring records + compact bytes, the accept flag (:427-457) and the status record.
 //
-// Phase A (lane = string): offsets, granule flags, final states of the tile's 32 strings (coalesced).
-// Phase B: the tile's rows of every sparse column are contiguous in memory: blanket zero-fill with 16-byte stores.
-// Phase C (lane = string): every lane scans the flagged granules of ITS string, in order.  A row's packed entries are
-//         looked up again from (byte, state) — one lookup replaces the reference's HashSet probes and `contains` scans —
-//         and give substr id, is_start, is_end(next row).  Non-zero values overwrite the zeros of phase B in L2.
-// Phase D (lane = string): accept flags and status records.
+// Rule of the memory traffic: never write PART of a sector that was completely written earlier (L2 streams full sectors
+// out early; a later partial write costs a DRAM read-modify-write).  Hence, per tile,
+//   fill  (warp)          the tile's rows of every sparse column are contiguous: blanket zero-fill, coalesced 16-byte stores;
+//   scan  (lane = string) each lane walks the flagged granules of ITS string in order: it rewrites the complete 32-byte
+//                         sector of the substr-id columns (values and zeros merged in registers), collects the bitmap
+//                         words, counts endpoint lookups and streams the boundaries of the mask algebra below, which
+//                         yields the masked segments, their records and compact bytes;
+//   masks (lane = string) rewrites the complete sectors of masked_chars / masked_substr_ids that a masked segment touches.
+// A row's packed entries are looked up again from (byte, state): one lookup replaces the reference's HashSet probes and
+// `contains` scans and gives substr id, is_start, is_end(next row).
+//
 // Masks.  With b_1 < b_2 < ... the rows where the id sum changes AND is_start_sum|is_end_sum is set, the forward scan
 //         (src/lib.rs:598-645) sets start_mask at b_k when is_start_sum[b_k] and resets it when only is_end_sum[b_k]; the
 //         backward scan (:663-714) sets end_mask for the rows before b_{k+1} when is_end_sum[b_{k+1}] and resets it when
 //         only is_start_sum[b_{k+1}].  Hence mask = 1 exactly on [b_k, b_{k+1}) with is_start at b_k and is_end at b_{k+1}.
-//         The boundaries are streamed in order; a closing boundary makes the lane overwrite the masked rows of
-//         [b_k, b_{k+1}) (they may extend over unflagged granules) — same L2 lines the warp has just zeroed.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -31,6 +31,7 @@ namespace b2r {
 
 constexpr uint32_t NO_POS = 0xFFFFFFFFu;
 constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_NSEG = 4;       // masked segments per string kept in registers; further ones take the patch path
 
 __device__ __forceinline__ uint32_t ent_sid(uint32_t e) { return (e >> ENT_SID_SHIFT) & 0xFFu; }
 
@@ -71,6 +72,18 @@ static __device__ __noinline__ void kill_string(const WalkParams& p, uint64_t id
     }
 }
 
+// warp-cooperative zero-fill of a contiguous region; base 16-byte aligned, bytes a multiple of 4
+__device__ __forceinline__ void emit_zero_region(uint8_t* base, uint64_t bytes, int lane) {
+    if (!base) return;
+    const uint32_t nv = (uint32_t)(bytes / 16);
+    uint4* q = reinterpret_cast<uint4*>(base) + lane;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint32_t v = lane;
+    for (; v + 96 < nv; v += 128, q += 128) { q[0] = z; q[32] = z; q[64] = z; q[96] = z; }
+    for (; v < nv; v += 32, q += 32) q[0] = z;
+    for (uint64_t o = (uint64_t)nv * 16 + (uint64_t)lane * 4; o < bytes; o += 128) *reinterpret_cast<uint32_t*>(base + o) = 0u;
+}
+
 // per-CTA view of the lookup tables (shared memory when they fit, else global) and the endpoint counters
 template <int D>
 struct EmitTables {
@@ -79,23 +92,23 @@ struct EmitTables {
     uint32_t* ep_s[D];          // shared-memory endpoint counters: [0,K*S) start lookups, [K*S,2*K*S) end lookups; null = global
 };
 
-// per-warp running sums published once at the end of the kernel
+// per-lane running sums published once at the end of the kernel
 struct EmitTotals {
     unsigned long long pad_rows = 0;
     uint32_t n_ok = 0, n_overlap = 0;
 };
 
-// rows [a,b) of string j are masked: start_mask = end_mask = 1 (src/lib.rs:740-764), b <= len.  Writes masked_chars,
-// masked_substr_ids, the compact bytes and one record per maximal run of a constant id sum.  Lane-private (one thread,
-// its own string).  Returns the updated (n_rec, n_cmp).
+// rows [a,b) of string j are masked (src/lib.rs:740-764), b <= len: the compact bytes and one record per maximal run of
+// a constant id sum; with `patch` instead masked_chars / masked_substr_ids, byte by byte (segments beyond EMIT_NSEG).
+// Lane-private.  Returns the updated (n_rec, n_cmp).
 template <int D, typename ST>
 static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const EmitTables<D> tb, uint64_t j, const uint8_t* src, uint32_t a, uint32_t b,
-                                                  uint32_t n_rec, uint32_t n_cmp) {
-    uint8_t* const mc = p.masked_chars ? p.masked_chars + j * p.row_pitch : nullptr;
-    uint8_t* const ms = p.masked_substr_ids ? p.masked_substr_ids + j * p.row_pitch : nullptr;
-    uint8_t* const cb = p.compact_bytes ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
+                                                  uint32_t n_rec, uint32_t n_cmp, bool patch) {
+    uint8_t* const mc = (patch && p.masked_chars) ? p.masked_chars + j * p.row_pitch : nullptr;
+    uint8_t* const ms = (patch && p.masked_substr_ids) ? p.masked_substr_ids + j * p.row_pitch : nullptr;
+    uint8_t* const cb = (!patch && p.compact_bytes) ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
     auto record = [&](uint32_t start, uint32_t len, uint32_t sid, uint32_t coff) {
-        if (p.records && n_rec < p.max_records) {
+        if (!patch && p.records && n_rec < p.max_records) {
             b2r_substr_record r; r.start = start; r.len = len; r.substr_id = sid; r.compact_off = coff;
             p.records[j * p.max_records + n_rec] = r;
         }
@@ -103,16 +116,16 @@ static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const Emi
     };
     uint32_t run_start = a, run_sum = 0;
     for (uint32_t i = a; i < b; i++) {
-        const uint32_t c = src[i];
+        const uint32_t c = __ldg(src + i);
         uint32_t sum = 0;
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t S = p.def[d].num_states;
-            const uint32_t s = (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[j * p.row_pitch + i];
+            const uint32_t s = (uint32_t)__ldcg(reinterpret_cast<const ST*>(p.def[d].states) + j * p.row_pitch + i);
             if (s < S) sum += ent_sid(tb.trans[d][(uint32_t)tb.cls[d][c] * S + s]);
         }
-        if (mc && !(p.debug & 16)) mc[i] = (uint8_t)c;
-        if (ms && sum && !(p.debug & 16)) ms[i] = (uint8_t)sum;
+        if (mc) mc[i] = (uint8_t)c;
+        if (ms) ms[i] = (uint8_t)sum;
         const uint32_t k = n_cmp + (i - a);
         if (cb && k < p.compact_pitch) cb[k] = (uint8_t)c;
         if (i == a) run_sum = sum;
@@ -125,52 +138,149 @@ static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const Emi
     return make_uint2(n_rec, n_cmp + (b - a));
 }
 
-// Lane-private scan of ONE string's flagged granules, in order (phase C).  Streams the boundaries of the mask algebra.
+// 16 rows of one string in registers: the bytes and the states of every def
 template <int D, typename ST>
-struct LaneScan {
+struct Granule {
+    uint32_t w[4];
+    uint32_t sv[D][4 * sizeof(ST)];
+    uint32_t n;                    // rows that are characters (1..16)
+
+    // granule g of string j (src = its first byte, L its length); 16*g < L
+    __device__ __forceinline__ void load(const WalkParams& p, uint64_t j, const uint8_t* src, uint32_t L, uint32_t g) {
+        const uint32_t base = 16 * g;
+        n = L - base < 16 ? L - base : 16;
+        // 16 bytes from an arbitrary address: two aligned 16-byte loads shifted into place; the second one is only
+        // touched when the bytes needed reach into it
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src + base);
+        const uint32_t sh = (uint32_t)(addr & 15);
+        const uint4* q = reinterpret_cast<const uint4*>(addr - sh);
+        const uint4 v0 = __ldg(q);
+        uint4 v1 = make_uint4(0, 0, 0, 0);
+        if (sh + n > 16) v1 = __ldg(q + 1);
+        const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t y[7], z[5];
+#pragma unroll
+        for (int k = 0; k < 7; k++) y[k] = (sh & 4) ? x[k + 1] : x[k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) z[k] = (sh & 8) ? y[k + 2] : y[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = __funnelshift_r(z[k], z[k + 1], (sh & 3) * 8);
+#pragma unroll
+        for (int d = 0; d < D; d++) {   // written by the walk (possibly by this very kernel): L2-coherent loads
+            const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const ST*>(p.def[d].states) + j * p.row_pitch + base);
+            const uint4 a = __ldcg(sp);
+            sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
+            if (sizeof(ST) == 2) { const uint4 b2 = __ldcg(sp + 1); sv[d][4 * (sizeof(ST) - 1)] = b2.x; sv[d][4 * (sizeof(ST) - 1) + 1] = b2.y; sv[d][4 * (sizeof(ST) - 1) + 2] = b2.z; sv[d][4 * (sizeof(ST) - 1) + 3] = b2.w; }
+        }
+    }
+    // compile-time row index
+    __device__ __forceinline__ uint32_t byte_at(int r) const { return (w[r >> 2] >> (8 * (r & 3))) & 0xFFu; }
+    __device__ __forceinline__ uint32_t state_at(int d, int r) const {
+        return sizeof(ST) == 1 ? (sv[d][r >> 2] >> (8 * (r & 3))) & 0xFFu : (sv[d][(r >> 1) % (4 * sizeof(ST))] >> (16 * (r & 1))) & 0xFFFFu;
+    }
+    // run-time row index
+    __device__ __forceinline__ uint32_t byte_dyn(uint32_t r) const {
+        const uint32_t q = r < 8 ? (r < 4 ? w[0] : w[1]) : (r < 12 ? w[2] : w[3]);
+        return (q >> (8 * (r & 3))) & 0xFFu;
+    }
+    __device__ __forceinline__ uint32_t state_dyn(int d, uint32_t r) const {
+        if (sizeof(ST) == 1) {
+            const uint32_t q = r < 8 ? (r < 4 ? sv[d][0] : sv[d][1]) : (r < 12 ? sv[d][2] : sv[d][3]);
+            return (q >> (8 * (r & 3))) & 0xFFu;
+        }
+        constexpr int H = 4 * (sizeof(ST) - 1);                           // 4 for 2-byte states (0 keeps the 1-byte instantiation in bounds)
+        const uint32_t lo = r < 4 ? (r < 2 ? sv[d][0] : sv[d][1]) : (r < 6 ? sv[d][2] : sv[d][3]);
+        const uint32_t hi = r < 12 ? (r < 10 ? sv[d][H] : sv[d][H + 1]) : (r < 14 ? sv[d][H + 2] : sv[d][H + 3]);
+        return ((r < 8 ? lo : hi) >> (16 * (r & 1))) & 0xFFFFu;
+    }
+};
+
+// The string a lane works on, and what the scan learns about it.
+template <int D, typename ST>
+struct LaneString {
     const WalkParams& p;
     const EmitTables<D>& tb;
     uint64_t j;
     const uint8_t* src;
     uint32_t L;
+    // results of the scan
+    uint32_t seg_a[EMIT_NSEG], seg_b[EMIT_NSEG], n_seg;   // masked segments [a,b), in order; n_seg may exceed EMIT_NSEG
+    uint32_t n_rec, n_cmp;
+    bool overlap, invalid;
+    // streaming state of the scan
     bool prev_valid, prev_is;   // last boundary: is_start_sum set there
     uint32_t prev_pos;
     uint32_t next_row;          // last examined row + 1; NO_POS = none yet / gap closed
     uint32_t carry_s, carry_ie; // id sum of row next_row-1, is_end_sum[next_row] (0 after a gap)
-    uint32_t n_rec, n_cmp;
-    bool overlap, invalid;
-    uint32_t bw_t, sw[D], ew[D];   // bitmap words being assembled: rows [32*bw_t, 32*bw_t+32)
+    uint32_t bw_t, sw[D], ew[D]; // bitmap words being assembled: rows [32*bw_t, 32*bw_t+32)
 
-    __device__ __forceinline__ LaneScan(const WalkParams& p_, const EmitTables<D>& tb_, uint64_t j_, const uint8_t* src_, uint32_t L_)
-        : p(p_), tb(tb_), j(j_), src(src_), L(L_) {
-        prev_valid = false; prev_is = false; prev_pos = 0;
-        next_row = NO_POS; carry_s = 0; carry_ie = 0;
-        n_rec = 0; n_cmp = 0; overlap = false; invalid = false;
-        bw_t = NO_POS;
-#pragma unroll
-        for (int d = 0; d < D; d++) { sw[d] = 0; ew[d] = 0; }
+    __device__ __forceinline__ LaneString(const WalkParams& p_, const EmitTables<D>& tb_, uint64_t j_, const uint8_t* src_, uint32_t L_)
+        : p(p_), tb(tb_), j(j_), src(src_), L(L_) {}
+
+    __device__ __forceinline__ uint32_t entry(int d, uint32_t c, uint32_t s) const {
+        const uint32_t S = p.def[d].num_states;
+        return s < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + s] : ENT_INVALID;   // state S = the trap state of the walk
     }
 
-    // a row where the id sum changes and is_start_sum | is_end_sum is set
+    // ---- scan ----------------------------------------------------------------------------------------------------------
+    template <bool PATCH>
     __device__ __forceinline__ void boundary(uint32_t pos, bool b_is, bool b_ie) {
-        if (prev_valid && prev_is && b_ie) {
-            const uint2 r = emit_segment<D, ST>(p, tb, j, src, prev_pos, pos, n_rec, n_cmp);
-            n_rec = r.x; n_cmp = r.y;
+        if (prev_valid && prev_is && b_ie) {                             // [prev_pos, pos) is masked
+            if (!PATCH || n_seg >= EMIT_NSEG) {
+                const uint2 r = emit_segment<D, ST>(p, tb, j, src, prev_pos, pos, n_rec, n_cmp, PATCH);
+                n_rec = r.x; n_cmp = r.y;
+            }
+#pragma unroll
+            for (int k = 0; k < EMIT_NSEG; k++)
+                if (n_seg == (uint32_t)k) { seg_a[k] = prev_pos; seg_b[k] = pos; }
+            n_seg++;
         }
         prev_valid = true; prev_pos = pos; prev_is = b_is;
     }
-    // the rows from next_row on are not examined (their granule is not flagged: id sum 0, no is_start) or lie past the end
-    // of the string; row next_row can still be a boundary: the id sum drops to 0 there and is_end_sum[next_row] comes from
-    // the row before
+    // the rows from next_row on are not examined (id sum 0 in every def, or past the end of the string); row next_row can
+    // still be a boundary: the id sum drops to 0 there and is_end_sum[next_row] comes from the row before
+    template <bool PATCH>
     __device__ __forceinline__ void close_gap() {
         if (next_row != NO_POS && carry_s != 0 && carry_ie != 0) {
             if (carry_ie > 1) overlap = true;
-            boundary(next_row, false, true);
+            boundary<PATCH>(next_row, false, true);
         }
         next_row = NO_POS; carry_s = 0; carry_ie = 0;
     }
+    // row i < L with byte c and states s[]; rows whose id sum is 0 in every def may be skipped
+    template <bool PATCH>
+    __device__ __forceinline__ void row(uint32_t i, uint32_t c, const uint32_t* s) {
+        if (next_row != i) close_gap<PATCH>();
+        uint32_t sum = 0, is_sum = 0, ie_next = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint32_t S = p.def[d].num_states;
+            const uint32_t e = entry(d, c, s[d]);
+            if (e & ENT_INVALID) { invalid = true; continue; }
+            const uint32_t sid = ent_sid(e);
+            if (!sid) continue;
+            sum += sid;
+            if (e & ENT_IS_START) {                                      // endpoint lookup src/lib.rs:235-258
+                is_sum++;
+                if (!PATCH) {
+                    const uint32_t bin = (sid - p.def[d].sid_offset) * S + s[d];
+                    if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + bin, 1u); else atomicAdd(p.def[d].ep_start + bin, 1ull);
+                }
+            }
+            if (e & ENT_IS_END) {                                        // endpoint lookup src/lib.rs:260-284
+                ie_next++;
+                if (!PATCH) {
+                    const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e & ENT_NEXT_MASK);
+                    if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + p.def[d].num_substrs * S + bin, 1u); else atomicAdd(p.def[d].ep_end + bin, 1ull);
+                }
+            }
+        }
+        if (is_sum > 1 || carry_ie > 1) overlap = true;
+        if (sum != carry_s && (is_sum | carry_ie)) boundary<PATCH>(i, is_sum != 0, carry_ie != 0);
+        carry_s = sum; carry_ie = ie_next; next_row = i + 1;
+    }
     __device__ __forceinline__ void flush_bitmap_words() {
-        if (bw_t == NO_POS || (p.debug & 16)) return;
+        if (bw_t == NO_POS) return;
 #pragma unroll
         for (int d = 0; d < D; d++) {
             if (sw[d] && p.def[d].start_enable) *reinterpret_cast<uint32_t*>(p.def[d].start_enable + j * p.bitmap_pitch + 4 * bw_t) = sw[d];
@@ -178,102 +288,120 @@ struct LaneScan {
             sw[d] = 0; ew[d] = 0;
         }
     }
-    // row i < L with byte c and states s[].  Rows with an id sum of 0 in every def may be skipped by the caller: they are
-    // treated like the rows of an unflagged granule.
-    __device__ __forceinline__ void row(uint32_t i, uint32_t c, const uint32_t* s) {
-        if (next_row != i) close_gap();
-        uint32_t sum = 0, is_sum = 0, ie_next = 0;
+    // flagged granule g; partner_flagged: the other granule of its 32-row window is flagged too (and writes itself)
+    template <bool PATCH>
+    __device__ __forceinline__ void scan_granule(uint32_t g, bool partner_flagged) {
+        Granule<D, ST> gr;
+        gr.load(p, j, src, L, g);
+        // pass 1, unrolled, all lanes in step: substr ids and flags of the 16 rows; which rows need the boundary logic?
+        uint32_t hot = 0, sidv[D][4], sb[D], eb[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint32_t S = p.def[d].num_states;
-            const uint32_t e = s[d] < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + s[d]] : ENT_INVALID;   // trap state: the walk parked this def
-            if (e & ENT_INVALID) { invalid = true; continue; }
-            const uint32_t sid = ent_sid(e);
-            if (!sid) continue;
-            sum += sid;
-            if (p.def[d].substr_ids && !(p.debug & 16)) p.def[d].substr_ids[j * p.row_pitch + i] = (uint8_t)sid;
-            if (e & ENT_IS_START) {                                      // start_enable, endpoint lookup src/lib.rs:235-258
-                is_sum++;
-                sw[d] |= 1u << (i & 31);
-                const uint32_t bin = (sid - p.def[d].sid_offset) * S + s[d];
-                if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + bin, 1u); else atomicAdd(p.def[d].ep_start + bin, 1ull);
-            }
-            if (e & ENT_IS_END) {                                        // end_enable, endpoint lookup src/lib.rs:260-284
-                ie_next++;
-                ew[d] |= 1u << (i & 31);
-                const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e & ENT_NEXT_MASK);
-                if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + p.def[d].num_substrs * S + bin, 1u); else atomicAdd(p.def[d].ep_end + bin, 1ull);
-            }
-        }
-        if (is_sum > 1 || carry_ie > 1) overlap = true;
-        if (sum != carry_s && (is_sum | carry_ie)) boundary(i, is_sum != 0, carry_ie != 0);
-        carry_s = sum; carry_ie = ie_next; next_row = i + 1;
-    }
-    // granule g: rows [16g, 16g+16)
-    __device__ __forceinline__ void granule(uint32_t g) {
-        const uint32_t base = 16 * g;
-        if ((g >> 1) != bw_t) { flush_bitmap_words(); bw_t = g >> 1; }
-        // 16 bytes of the string from an arbitrary address: two aligned 16-byte loads, shifted into place.  The second
-        // one is only touched when the bytes needed reach into it.
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(src + base);
-        const uint32_t sh = (uint32_t)(addr & 15);
-        const uint32_t n = L - base < 16 ? L - base : 16;              // rows of this granule that are characters (>= 1)
-        const uint4* q = reinterpret_cast<const uint4*>(addr - sh);
-        const uint4 v0 = __ldg(q);
-        uint4 v1 = make_uint4(0, 0, 0, 0);
-        if (sh + n > 16) v1 = __ldg(q + 1);
-        uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t y[7], z[5], w[4];
-#pragma unroll
-        for (int k = 0; k < 7; k++) y[k] = (sh & 4) ? x[k + 1] : x[k];
-#pragma unroll
-        for (int k = 0; k < 5; k++) z[k] = (sh & 8) ? y[k + 2] : y[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = __funnelshift_r(z[k], z[k + 1], (sh & 3) * 8);
-        uint32_t sv[D][4 * sizeof(ST)];
-#pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const ST*>(p.def[d].states) + j * p.row_pitch + base);
-            const uint4 a = __ldg(sp);
-            sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
-            if (sizeof(ST) == 2) { const uint4 b2 = __ldg(sp + 1); sv[d][4] = b2.x; sv[d][5] = b2.y; sv[d][6] = b2.z; sv[d][7] = b2.w; }
-        }
-        // pass 1, unrolled, all lanes in step: which rows carry a substr id (or an invalid transition)?
-        uint32_t hot = 0;
+        for (int d = 0; d < D; d++) { sb[d] = 0; eb[d] = 0; sidv[d][0] = sidv[d][1] = sidv[d][2] = sidv[d][3] = 0; }
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const uint32_t c = (w[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+            const uint32_t c = gr.byte_at(r);
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                const uint32_t S = p.def[d].num_states;
-                const uint32_t st = sizeof(ST) == 1 ? (sv[d][r >> 2] >> (8 * (r & 3))) & 0xFFu : (sv[d][r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
-                const uint32_t e = st < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + st] : ENT_INVALID;
+                uint32_t e = entry(d, c, gr.state_at(d, r));
+                if ((uint32_t)r >= gr.n) e = 0;                          // rows past the end of the string are not characters
                 if (e & (ENT_SID_MASK | ENT_INVALID)) hot |= 1u << r;
+                if (!PATCH) {
+                    sidv[d][r >> 2] |= ent_sid(e) << (8 * (r & 3));
+                    sb[d] |= ((e >> 24) & 1u) << r;
+                    eb[d] |= ((e >> 25) & 1u) << r;
+                }
             }
         }
-        hot &= (1u << n) - 1u;                                           // rows past the end of the string are not characters
+        if (!PATCH) {
+            // the complete sector of the substr-id columns: my 16 bytes, and zeros for the partner unless it writes itself
+            const uint32_t base = 16 * g, pbase = 16 * (g ^ 1u);
+            const bool partner = !partner_flagged && (uint64_t)pbase + 16 <= p.row_pitch;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                if (!p.def[d].substr_ids) continue;
+                uint8_t* const row = p.def[d].substr_ids + j * p.row_pitch;
+                *reinterpret_cast<uint4*>(row + base) = make_uint4(sidv[d][0], sidv[d][1], sidv[d][2], sidv[d][3]);
+                if (partner) *reinterpret_cast<uint4*>(row + pbase) = make_uint4(0, 0, 0, 0);
+            }
+            if ((g >> 1) != bw_t) { flush_bitmap_words(); bw_t = g >> 1; }
+#pragma unroll
+            for (int d = 0; d < D; d++) { sw[d] |= sb[d] << (16 * (g & 1)); ew[d] |= eb[d] << (16 * (g & 1)); }
+        }
         // pass 2, one loop body shared by all lanes: each lane handles ITS next hot row
         while (hot) {
             const uint32_t r = (uint32_t)__ffs((int)hot) - 1u;
             hot &= hot - 1;
-            const uint32_t wq = r < 8 ? (r < 4 ? w[0] : w[1]) : (r < 12 ? w[2] : w[3]);
-            const uint32_t c = (wq >> (8 * (r & 3))) & 0xFFu;
             uint32_t st[D];
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                if (sizeof(ST) == 1) {
-                    const uint32_t q = r < 8 ? (r < 4 ? sv[d][0] : sv[d][1]) : (r < 12 ? sv[d][2] : sv[d][3]);
-                    st[d] = (q >> (8 * (r & 3))) & 0xFFu;
-                } else {
-                    const uint32_t lo = r < 4 ? (r < 2 ? sv[d][0] : sv[d][1]) : (r < 6 ? sv[d][2] : sv[d][3]);
-                    const uint32_t hi = r < 12 ? (r < 10 ? sv[d][4 * (sizeof(ST) - 1)] : sv[d][4 * (sizeof(ST) - 1) + 1]) : (r < 14 ? sv[d][4 * (sizeof(ST) - 1) + 2] : sv[d][4 * (sizeof(ST) - 1) + 3]);
-                    st[d] = ((r < 8 ? lo : hi) >> (16 * (r & 1))) & 0xFFFFu;
-                }
-            }
-            row(base + r, c, st);
+            for (int d = 0; d < D; d++) st[d] = gr.state_dyn(d, r);
+            row<PATCH>(16 * g + r, gr.byte_dyn(r), st);
         }
     }
-    __device__ __forceinline__ void finish() { close_gap(); flush_bitmap_words(); }
+    // fw0 / fw1: granule flags 0..63 of this string; further words come from the flag buffer `flags`
+    template <bool PATCH>
+    __device__ __forceinline__ void scan(uint32_t fw0, uint32_t fw1, const uint32_t* flags) {
+        n_seg = 0; n_rec = 0; n_cmp = 0; overlap = false; invalid = false;
+        prev_valid = false; prev_is = false; prev_pos = 0;
+        next_row = NO_POS; carry_s = 0; carry_ie = 0;
+        bw_t = NO_POS;
+#pragma unroll
+        for (int d = 0; d < D; d++) { sw[d] = 0; ew[d] = 0; }
+        for (uint32_t w = 0; w < p.fm_words && !invalid; w++) {
+            const uint32_t fw = w == 0 ? fw0 : w == 1 ? fw1 : __ldcg(flags + (size_t)w * p.n_strings + j);
+            uint32_t bits = fw;
+            while (bits && !invalid) {
+                const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
+                bits &= bits - 1;
+                scan_granule<PATCH>(w * 32 + g, (fw >> (g ^ 1u)) & 1u);
+            }
+        }
+        if (!invalid) { close_gap<PATCH>(); if (!PATCH) flush_bitmap_words(); }
+    }
+
+    // ---- masks ---------------------------------------------------------------------------------------------------------
+    // bit r set: row 16g + r lies inside one of the first EMIT_NSEG masked segments
+    __device__ __forceinline__ uint32_t masked_rows(uint32_t g) const {
+        const uint32_t base = 16 * g;
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < EMIT_NSEG; k++) {
+            if ((uint32_t)k < n_seg && seg_b[k] > base && seg_a[k] < base + 16) {
+                const uint32_t lo = seg_a[k] > base ? seg_a[k] - base : 0u;
+                const uint32_t hi = seg_b[k] < base + 16 ? seg_b[k] - base : 16u;
+                m |= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            }
+        }
+        return m;
+    }
+    // window t = rows [32t, 32t+32), reached by a masked segment: the complete sector of masked_chars / masked_substr_ids
+    __device__ __forceinline__ void write_masked_window(uint32_t t) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t g = 2 * t + h;
+            const uint32_t base = 16 * g;
+            if ((uint64_t)base + 16 > p.row_pitch) continue;             // past the row (the last window of a row can be half)
+            uint32_t mcv[4] = {0, 0, 0, 0}, msv[4] = {0, 0, 0, 0};
+            const uint32_t mrows = base < L ? masked_rows(g) : 0u;
+            if (mrows) {
+                Granule<D, ST> gr;
+                gr.load(p, j, src, L, g);
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    const uint32_t c = gr.byte_at(r);
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        const uint32_t e = entry(d, c, gr.state_at(d, r));
+                        sum += (e & ENT_INVALID) ? 0u : ent_sid(e);
+                    }
+                    if ((mrows >> r) & 1u) { mcv[r >> 2] |= c << (8 * (r & 3)); msv[r >> 2] |= sum << (8 * (r & 3)); }
+                }
+            }
+            const uint64_t o = j * p.row_pitch + base;
+            if (p.masked_chars) *reinterpret_cast<uint4*>(p.masked_chars + o) = make_uint4(mcv[0], mcv[1], mcv[2], mcv[3]);
+            if (p.masked_substr_ids) *reinterpret_cast<uint4*>(p.masked_substr_ids + o) = make_uint4(msv[0], msv[1], msv[2], msv[3]);
+        }
+    }
 };
 
 // Warp-cooperative emitter for one tile of 32 consecutive strings.
@@ -285,76 +413,62 @@ struct TileEmitter {
 
     __device__ __forceinline__ TileEmitter(const WalkParams& p_, const EmitTables<D>& tb_, int lane_) : p(p_), tb(tb_), lane(lane_) {}
 
-    // One tile.  Phase A (lane = string): offsets, granule flags, final states.  Phase B: the tile's rows of every sparse
-    // column are contiguous — blanket zero-fill with 16-byte stores.  Phase C (lane = string): every lane scans the flagged
-    // granules of its own string.  Phase D (lane = string): accept rule (src/lib.rs:427-457) and the status records.
-    __device__ __forceinline__ void run_tile(uint64_t tile, EmitTotals& tot) {
+    // Lane = string.  off / Ll / live: the lane's string (live = in range and not too long); fw0 / fw1: its granule flags
+    // 0..63 (further words are read from p.fmask); fin[]: its final states; filled: the caller has zeroed the tile's rows.
+    __device__ __forceinline__ void run_tile(uint64_t tile_base, bool valid, bool live, uint64_t off, uint32_t Ll, uint32_t fw0, uint32_t fw1,
+                                             const uint32_t* fin, EmitTotals& tot, bool filled) {
+        constexpr uint32_t FULL = 0xffffffffu;
         const uint64_t N = p.n_strings;
         const uint32_t M = p.max_chars;
         const uint64_t rp = p.row_pitch, bp = p.bitmap_pitch;
-        const uint64_t tile_base = tile * 32;
         const uint64_t jl = tile_base + lane;
-        const bool valid = jl < N;
         const uint64_t rows_here = N - tile_base < 32 ? N - tile_base : 32;
 
-        // ---- A ----------------------------------------------------------------------------------------------------
-        uint64_t off = 0, end = 0;
-        if (valid) { off = p.offsets[jl]; end = p.offsets[jl + 1]; }
-        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // SURVEY 8(a) row 6: len must be <= M-1
-        const bool live = valid && !too_long;
-        const uint32_t Ll = live ? (uint32_t)(end - off) : 0u;
-        uint32_t fw0 = 0, fw1 = 0;
-        if (live && p.fm_words > 0) fw0 = __ldg(p.fmask + jl);
-        if (live && p.fm_words > 1) fw1 = __ldg(p.fmask + N + jl);
-        uint32_t fin[D];
+        // ---- fill (warp): the tile's rows of a column are contiguous ----------------------------------------------------
+        if (!filled && !(p.debug & 1)) {
 #pragma unroll
-        for (int d = 0; d < D; d++) fin[d] = (live && !(p.debug & 4)) ? (uint32_t) reinterpret_cast<const ST*>(p.def[d].states)[jl * rp + Ll] : 0xFFFFFFFEu;
-
-        // ---- B ----------------------------------------------------------------------------------------------------
-        auto zero_region = [&](uint8_t* base, uint64_t bytes) {   // base 16-byte aligned, bytes a multiple of 4
-            if (!base || (p.debug & 1)) return;
-            const uint64_t nv = bytes / 16;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint64_t v = lane; v < nv; v += 32) reinterpret_cast<uint4*>(base)[v] = z;
-            for (uint64_t o = nv * 16 + (uint64_t)lane * 4; o < bytes; o += 128) *reinterpret_cast<uint32_t*>(base + o) = 0u;
-        };
-        auto phase_b = [&]() {
-#pragma unroll
-        for (int d = 0; d < D; d++) {
-            zero_region(p.def[d].substr_ids ? p.def[d].substr_ids + tile_base * rp : nullptr, rows_here * rp);
-            zero_region(p.def[d].start_enable ? p.def[d].start_enable + tile_base * bp : nullptr, rows_here * bp);
-            zero_region(p.def[d].end_enable ? p.def[d].end_enable + tile_base * bp : nullptr, rows_here * bp);
+            for (int d = 0; d < D; d++) {
+                emit_zero_region(p.def[d].substr_ids ? p.def[d].substr_ids + tile_base * rp : nullptr, rows_here * rp, lane);
+                emit_zero_region(p.def[d].start_enable ? p.def[d].start_enable + tile_base * bp : nullptr, rows_here * bp, lane);
+                emit_zero_region(p.def[d].end_enable ? p.def[d].end_enable + tile_base * bp : nullptr, rows_here * bp, lane);
+            }
+            emit_zero_region(p.masked_chars ? p.masked_chars + tile_base * rp : nullptr, rows_here * rp, lane);
+            emit_zero_region(p.masked_substr_ids ? p.masked_substr_ids + tile_base * rp : nullptr, rows_here * rp, lane);
         }
-        zero_region(p.masked_chars ? p.masked_chars + tile_base * rp : nullptr, rows_here * rp);
-        zero_region(p.masked_substr_ids ? p.masked_substr_ids + tile_base * rp : nullptr, rows_here * rp);
-            __syncwarp();                                                // the zeros are ordered before the values of phase C
-        };
-        if (!(p.debug & 32)) phase_b();
+        __syncwarp();                                                    // the zeros are ordered before the values below
 
-        // ---- C ----------------------------------------------------------------------------------------------------
+        // ---- scan + masks (lane = string) ---------------------------------------------------------------------------------
         uint32_t r_nrec = 0, r_ncmp = 0, r_flags = 0;
+        bool patch = false;
+        LaneString<D, ST> ls(p, tb, jl, p.bytes + off, Ll);
         if (live && !(p.debug & 2) && (p.fm_words > 2 || (fw0 | fw1) != 0)) {
-            LaneScan<D, ST> sc(p, tb, jl, p.bytes + off, Ll);
-            for (uint32_t w = 0; w < p.fm_words && !sc.invalid; w++) {
-                uint32_t bits = w == 0 ? fw0 : w == 1 ? fw1 : __ldg(p.fmask + (size_t)w * N + jl);
-                while (bits && !sc.invalid) {
-                    const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
-                    bits &= bits - 1;
-                    sc.granule(w * 32 + g);
+            ls.template scan<false>(fw0, fw1, p.fmask);
+            if (ls.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
+            else {
+                r_nrec = ls.n_rec; r_ncmp = ls.n_cmp;
+                if (ls.overlap) r_flags = B2R_ST_OVERLAP;
+                patch = ls.n_seg > EMIT_NSEG;
+                uint32_t last_t = NO_POS;
+#pragma unroll
+                for (int k = 0; k < EMIT_NSEG; k++) {
+                    if ((uint32_t)k >= ls.n_seg) continue;
+                    for (uint32_t t = ls.seg_a[k] >> 5; t <= (ls.seg_b[k] - 1) >> 5; t++) {
+                        if (t == last_t) continue;                       // written with the previous segment (all segments of a window go together)
+                        last_t = t;
+                        ls.write_masked_window(t);
+                    }
                 }
             }
-            if (sc.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
-            else {
-                sc.finish();
-                r_nrec = sc.n_rec; r_ncmp = sc.n_cmp;
-                if (sc.overlap) r_flags = B2R_ST_OVERLAP;
-            }
+        }
+        // ---- more masked segments than the registers hold: patch their rows byte by byte (rare) ------------------------------
+        if (__any_sync(FULL, patch)) {
+            __syncwarp();
+            if (patch) ls.template scan<true>(fw0, fw1, p.fmask);
         }
 
-        if (p.debug & 32) phase_b();
-        // ---- D ----------------------------------------------------------------------------------------------------
+        // ---- accept rule (src/lib.rs:427-457), status records (lane = string) --------------------------------------------
         if (valid && !(p.debug & 8)) {
-            if (too_long || (r_flags & B2R_ST_INVALID_TRANSITION)) kill_string(p, jl);
+            if (!live || (r_flags & B2R_ST_INVALID_TRANSITION)) kill_string(p, jl);
             else {
                 uint32_t flags = r_flags;
 #pragma unroll
@@ -372,10 +486,38 @@ struct TileEmitter {
         }
         __syncwarp();
     }
+
+    // stand-alone entry: everything about the tile's strings comes from global memory
+    __device__ __forceinline__ void run_tile_from_memory(uint64_t tile, EmitTotals& tot) {
+        const uint64_t N = p.n_strings;
+        const uint32_t M = p.max_chars;
+        const uint64_t tile_base = tile * 32;
+        const uint64_t jl = tile_base + lane;
+        const bool valid = jl < N;
+        uint64_t off = 0, end = 0;
+        if (valid) { off = p.offsets[jl]; end = p.offsets[jl + 1]; }
+        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // SURVEY 8(a) row 6: len must be <= M-1
+        const bool live = valid && !too_long;
+        const uint32_t Ll = live ? (uint32_t)(end - off) : 0u;
+        uint32_t fw0 = 0, fw1 = 0;
+        if (live && p.fm_words > 0) fw0 = __ldcg(p.fmask + jl);
+        if (live && p.fm_words > 1) fw1 = __ldcg(p.fmask + N + jl);
+        uint32_t fin[D];
+#pragma unroll
+        for (int d = 0; d < D; d++)
+            fin[d] = (live && !(p.debug & 4)) ? (uint32_t)__ldcg(reinterpret_cast<const ST*>(p.def[d].states) + jl * p.row_pitch + Ll) : 0xFFFFFFFEu;
+        run_tile(tile_base, valid, live, live ? off : 0ull, Ll, fw0, fw1, fin, tot, /*filled=*/p.prefilled != 0);
+    }
 };
 
-// shared memory of the emitter: endpoint counters, then (optionally) the lookup tables.  Every thread of the CTA calls
-// this, followed by a __syncthreads().
+// shared memory of the emitter: endpoint counters, then (optionally) the lookup tables.
+__host__ __device__ inline uint32_t emit_smem_bytes(const WalkParams& p) {
+    uint32_t n = (p.ep_smem_bytes + 15u) & ~15u;
+    if (p.emit_smem_tables)
+        for (uint32_t d = 0; d < p.n_defs; d++) n += ((p.def[d].num_classes * p.def[d].num_states * 4u + 256u) + 15u) & ~15u;
+    return n;
+}
+// Every thread of the CTA calls this, followed by a __syncthreads().
 template <int D>
 __device__ __forceinline__ void emit_tables_init(const WalkParams& p, unsigned char* esmem, EmitTables<D>& tb) {
     uint32_t off = 0;
@@ -392,10 +534,9 @@ __device__ __forceinline__ void emit_tables_init(const WalkParams& p, unsigned c
             const uint32_t n = p.def[d].num_classes * p.def[d].num_states;
             uint32_t* const t = reinterpret_cast<uint32_t*>(esmem + off);
             for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) t[i] = p.def[d].trans[i];
-            off += n * 4;
-            uint8_t* const c = esmem + off;
+            uint8_t* const c = esmem + off + n * 4;
             for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) c[i] = p.def[d].byte_class[i];
-            off += 256;
+            off += ((n * 4 + 256u) + 15u) & ~15u;
             tb.trans[d] = t; tb.cls[d] = c;
         } else {
             tb.trans[d] = p.def[d].trans; tb.cls[d] = p.def[d].byte_class;
@@ -435,11 +576,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
     emit_tables_init<D>(p, esmem, tb);
     __syncthreads();
 
-    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     TileEmitter<D, ST> em(p, tb, lane);
     EmitTotals tot;
-    for (uint64_t tile = gw; tile < p.n_tiles; tile += warps_total) em.run_tile(tile, tot);
+    for (;;) {   // tiles handed out by an atomic counter: the work per tile varies with the strings
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&p.counters->emit_tile_counter, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= p.n_tiles) break;
+        em.run_tile_from_memory(t, tot);
+    }
     emit_publish<D>(p, tb, tot);
 }
 

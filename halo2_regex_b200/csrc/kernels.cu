@@ -131,13 +131,6 @@ int launch_walk(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen
     return B2R_ERR_UNSUPPORTED;
 }
 
-size_t emit_smem_bytes(const WalkParams& p) {
-    size_t n = (p.ep_smem_bytes + 15u) & ~15u;
-    if (p.emit_smem_tables)
-        for (uint32_t d = 0; d < p.n_defs; d++) n += (size_t)p.def[d].num_classes * p.def[d].num_states * 4 + 256;
-    return n;
-}
-
 int launch_emit(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen) {
     int n_sm = 0, max_smem = 0;
     int rc = device_limits(&n_sm, &max_smem);

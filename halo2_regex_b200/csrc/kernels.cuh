@@ -40,7 +40,8 @@ struct BatchCounters {               // zeroed (first_bad = ~0) before every bat
     unsigned long long pad_rows;     // sum over strings of (M - len): multiplicity of table row 0
     unsigned long long n_ok_strings; // strings that were processed to the end
     unsigned long long tile_counter; // next tile of 32 strings to hand out (dynamic scheduling of the persistent walk CTAs)
-    unsigned long long reserved[3];
+    unsigned long long emit_tile_counter;   // the same for emit_kernel
+    unsigned long long reserved[2];
 };
 
 struct WalkParams {
@@ -68,6 +69,8 @@ struct WalkParams {
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
     uint32_t emit_smem_tables;       // 1: emit_kernel stages byte_class / trans in shared memory
+    uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
+    uint32_t prefilled;              // 1: the sparse columns were zeroed before emit_kernel (memset on a side stream, overlapping the walk)
     uint32_t debug;                  // timing experiments only (B2R_DEBUG env): emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status
 };
 

@@ -32,6 +32,7 @@
 #include <cstdint>
 
 #include "defs.hpp"
+#include "emit.cuh"
 #include "kernels.cuh"
 
 namespace b2r {
@@ -39,6 +40,7 @@ namespace b2r {
 constexpr int WALK_MAX_THREADS = 512;
 constexpr int WALK_DCH = 32;                       // positions per staged chunk
 constexpr int WALK_PITCH = WALK_DCH + 16;          // input tile row pitch (bytes): 3 x 16 B keeps per-lane LDS.128 conflict-free
+constexpr uint32_t WALK_ZERO_BYTES = 4096;         // shared zero buffer, source of the TMA bulk zero-fills (fused emit stage)
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------------
 // prmt (default mode): selector nibble 0-7 picks a byte of {a (0-3), b (4-7)}
@@ -79,6 +81,8 @@ struct WalkLayout {
     uint32_t tab[B2R_MAX_DEFS];    // byte offsets from the aligned base; table rows are P*stride bytes and aligned to that
     uint32_t cls;                  // 256 entries of `stride` bytes
     uint32_t hist[B2R_MAX_DEFS];   // (S+1) x 256 u32 bins per def
+    uint32_t emit;                 // emit tables + endpoint counters (emit.cuh), fused mode
+    uint32_t zero;                 // WALK_ZERO_BYTES of zeros, fused mode
     uint32_t tiles;                // first per-warp tile
     uint32_t per_warp;
     uint32_t align;                // alignment the base needs (the largest table row)
@@ -102,6 +106,11 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
     if (p.hist_mode == HIST_SMEM)
         for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
     cur = walk_align_up(cur, 16);
+    L.emit = cur;
+    if (p.fuse) cur += emit_smem_bytes(p);
+    cur = walk_align_up(cur, 128);
+    L.zero = cur;
+    if (p.fuse) cur += WALK_ZERO_BYTES;
     L.tiles = cur;
     L.per_warp = 2 * 32 * WALK_PITCH + p.n_defs * 32 * (WALK_DCH * state_bytes + 16);
     L.align = al;
@@ -161,7 +170,16 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         for (int d = 0; d < D; d++)
             for (uint32_t i = threadIdx.x; i < (p.def[d].num_states + 1) * 256u; i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
     }
+    EmitTables<D> etb;
+    const uint32_t zero_s = base_s + lay.zero;
+    if (p.fuse) {
+        emit_tables_init<D>(p, dsmem + (base_s - smem_u32(dsmem)) + lay.emit, etb);
+        for (uint32_t i = threadIdx.x * 16; i < WALK_ZERO_BYTES; i += blockDim.x * 16) sts128(zero_s + i, 0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zero buffer -> visible to the TMA (async proxy)
+    }
     __syncthreads();
+    TileEmitter<D, ST> emitter(p, etb, lane);
+    EmitTotals tot;
 
     const uint32_t M = p.max_chars;
     const uint32_t Mpad = (M + 15u) & ~15u;                             // rows written (row_pitch >= Mpad by contract)
@@ -208,7 +226,8 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         const bool valid = idx < p.n_strings;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[idx]; end = p.offsets[idx + 1]; }
-        if (end < off || end - off > (uint64_t)(M - 1)) end = off;      // too long: emit reports it; walk nothing
+        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // emit reports it; walk nothing
+        if (too_long) end = off;
         const uint32_t L = (uint32_t)(end - off);
         const uint32_t rows_here = (p.n_strings - tile_base < 32) ? (uint32_t)(p.n_strings - tile_base) : 32u;
 
@@ -243,8 +262,39 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             cp_async_commit();
         };
         stage(0);
+        // fused emit stage, fill: the tile's rows of every sparse column are contiguous.  Zero them with TMA bulk stores from
+        // the shared zero buffer, one per lane, now; they complete in the background while the tile is walked (ordinary
+        // stores would queue in the LSU in front of the other warps' table lookups).
+        if (p.fuse && !(p.debug & 1)) {
+            const uint64_t cbytes = (uint64_t)rows_here * rp, bbytes = (uint64_t)rows_here * p.bitmap_pitch;
+            uint8_t* reg_ptr[3 * D + 2];
+            uint64_t reg_bytes[3 * D + 2];
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                reg_ptr[3 * d] = p.def[d].substr_ids ? p.def[d].substr_ids + tile_base * rp : nullptr; reg_bytes[3 * d] = cbytes;
+                reg_ptr[3 * d + 1] = p.def[d].start_enable ? p.def[d].start_enable + tile_base * p.bitmap_pitch : nullptr; reg_bytes[3 * d + 1] = bbytes;
+                reg_ptr[3 * d + 2] = p.def[d].end_enable ? p.def[d].end_enable + tile_base * p.bitmap_pitch : nullptr; reg_bytes[3 * d + 2] = bbytes;
+            }
+            reg_ptr[3 * D] = p.masked_chars ? p.masked_chars + tile_base * rp : nullptr; reg_bytes[3 * D] = cbytes;
+            reg_ptr[3 * D + 1] = p.masked_substr_ids ? p.masked_substr_ids + tile_base * rp : nullptr; reg_bytes[3 * D + 1] = cbytes;
+            uint32_t first = 0;                                         // ops are numbered region by region; lane takes ops lane, lane+32, ...
+#pragma unroll
+            for (int r = 0; r < 3 * D + 2; r++) {
+                if (!reg_ptr[r]) continue;
+                const uint32_t bulk_bytes = (uint32_t)(reg_bytes[r] & ~15ull);   // bitmap regions of a partial tile can end on a 4-byte boundary
+                const uint32_t n_ops = (bulk_bytes + WALK_ZERO_BYTES - 1) / WALK_ZERO_BYTES;
+                for (uint32_t op = (lane + 32u - (first & 31u)) & 31u; op < n_ops; op += 32) {
+                    const uint32_t o = op * WALK_ZERO_BYTES;
+                    const uint32_t nb = bulk_bytes - o < WALK_ZERO_BYTES ? bulk_bytes - o : WALK_ZERO_BYTES;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reg_ptr[r] + o), "r"(zero_s), "r"(nb) : "memory");
+                }
+                for (uint64_t o = bulk_bytes + (uint64_t)lane * 4; o < reg_bytes[r]; o += 128) *reinterpret_cast<uint32_t*>(reg_ptr[r] + o) = 0u;
+                first += n_ops;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
 
-        uint32_t fm = 0;                                                // granule flags of the current group of 32 granules
+        uint32_t fm = 0, fw0 = 0, fw1 = 0;                              // granule flags: current group of 32 granules, words 0 and 1
 #pragma unroll 1
         for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
             const uint32_t cbase = chunk * DCH;
@@ -359,12 +409,23 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             const uint32_t gcount = (chunk + 1) * (DCH / 16);
             if ((gcount & 31u) == 0 || chunk + 1 == n_chunks) {
                 const uint32_t wi = (gcount - 1) >> 5;
-                if (valid && wi < p.fm_words) p.fmask[(size_t)wi * p.n_strings + idx] = fm;
+                if (wi == 0) fw0 = fm; else if (wi == 1) fw1 = fm;
+                if (valid && wi < p.fm_words && (!p.fuse || wi >= 2)) p.fmask[(size_t)wi * p.n_strings + idx] = fm;
                 fm = 0;
             }
             __syncwarp();
         }
+        // ---- fused emit stage: the tile's states are in L1/L2, its flags and final states in registers --------------------
+        if (p.fuse) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my zero-fill stores have completed ...
+            __syncwarp();                                                 // ... and so have those of the other lanes
+            uint32_t fin[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) fin[d] = cur[d] >> 16;
+            emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true);
+        }
     }
+    if (p.fuse) emit_publish<D>(p, etb, tot);
 
     // ---- flush the multiplicity bins: bin (s,c) of def d -> dense global histogram [c*S + s] -------------------------------
     if (HM == (int)HIST_SMEM) {

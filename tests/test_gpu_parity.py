@@ -223,7 +223,7 @@ def test_device_pointer_entry_point():
         out = H.DeviceOutputs(cfg, len(strings), max_records=8, compact_pitch=64)
         cfg.match_batch_device(d_bytes, d_offs, out, stream=stream)
         res = cfg.batch_result(stream=stream)
-    assert res.code == 0 and cfg.last_launch_count() == 3      # walk, emit, finalize
+    assert res.code == 0 and cfg.last_launch_count() == 2      # walk (emit stage fused in), finalize
     o, _ = ocfg.match_batch(data, offs, max_records=8, compact_pitch=64)
     assert H.compare_outputs(out.to_host(), o) == []
 
@@ -240,6 +240,16 @@ def test_table_and_bin_placements(monkeypatch, set_name, table_mode, hist_mode):
     cfg, g, o = _both(set_name, 261, strings)
     if not (set_name == "three" and table_mode == "repl"):      # three replicated tables exceed shared memory: the launcher says so
         assert cfg.last_plan()[0] == table_mode
+
+
+@pytest.mark.parametrize("set_name", ["regex1", "test1", "regex3_k3"])
+def test_separate_emit_kernel(monkeypatch, set_name):
+    """B2R_FUSE=0: the emit stage as its own kernel after the walk (the default runs it inside walk_kernel, tile by tile)."""
+    monkeypatch.setenv("B2R_FUSE", "0")
+    rng = random.Random(zlib.crc32(set_name.encode()) + 7)
+    strings = _random_strings(rng, 500, 300, SNIPPETS) + [b"", b"zz"]
+    cfg, g, o = _both(set_name, 301, strings)
+    assert cfg.last_launch_count() == 3
 
 
 def test_wide_state_column():
