@@ -170,6 +170,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
         DefDev& dd = p.def[d];
         dd.byte_class = c->dev[d].byte_class; dd.trans = c->dev[d].trans; dd.hot = c->dev[d].hot;
         dd.padded_states = padded_states(pd.num_states);
+        dd.hot_states[0] = pd.hot_states[0]; dd.hot_states[1] = pd.hot_states[1];
         dd.num_states = pd.num_states; dd.num_classes = pd.num_classes; dd.first_state = pd.first_state;
         dd.accepted_state = pd.accepted_state; dd.sid_offset = pd.substr_id_offset; dd.num_substrs = pd.num_substrs;
         dd.hist = c->dev[d].hist; dd.ep_start = c->dev[d].ep_start; dd.ep_end = c->dev[d].ep_end;

@@ -194,9 +194,12 @@ int pack_def(const AllstrDef& a, const std::vector<const SubstrDef*>& substrs, u
             }
         }
         dense[(size_t)t.ch * S + t.cur] = (uint32_t)t.next | (sid << ENT_SID_SHIFT) | flags;
+        if (sid && t.cur < 64) out.hot_states[t.cur >> 5] |= 1u << (t.cur & 31);
         out.rows.push_back({t.ch, t.cur, t.next, sid});
         out.row_bin.push_back((uint32_t)t.ch * S + (uint32_t)t.cur);
     }
+
+    if (S < 64) out.hot_states[S >> 5] |= 1u << (S & 31);   // the walk's trap state (after an invalid transition) must be looked at
 
     // byte equivalence classes: bytes with identical [S] columns share a class
     out.byte_class.assign(256, 0);

@@ -59,6 +59,7 @@ struct PackedDef {
     uint32_t state_width = 1;     // bytes per state in the state column
     uint32_t substr_id_offset = 1, num_substrs = 0;
     uint32_t num_classes = 0;     // byte equivalence classes incl. the all-invalid class (if any byte has no edge)
+    uint32_t hot_states[2] = {0, 0};   // bit s: some transition out of state s (< 64) carries a substr id
     std::vector<uint8_t> byte_class;   // [256]
     std::vector<uint32_t> trans;       // [num_classes][num_states]
     std::vector<TableRow> rows;        // RegexTableConfig::load order; rows[0] = (0,dummy,dummy,0)

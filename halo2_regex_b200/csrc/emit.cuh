@@ -98,17 +98,17 @@ struct EmitTotals {
     uint32_t n_ok = 0, n_overlap = 0;
 };
 
-// rows [a,b) of string j are masked (src/lib.rs:740-764), b <= len: the compact bytes and one record per maximal run of
-// a constant id sum; with `patch` instead masked_chars / masked_substr_ids, byte by byte (segments beyond EMIT_NSEG).
-// Lane-private.  Returns the updated (n_rec, n_cmp).
+// Overflow path (a string with more than EMIT_NSEG masked segments): rows [a,b) of string j are masked
+// (src/lib.rs:740-764), b <= len: masked_chars / masked_substr_ids byte by byte, the compact bytes and one record per
+// maximal run of a constant id sum.  Lane-private.  Returns the updated (n_rec, n_cmp).
 template <int D, typename ST>
 static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const EmitTables<D> tb, uint64_t j, const uint8_t* src, uint32_t a, uint32_t b,
-                                                  uint32_t n_rec, uint32_t n_cmp, bool patch) {
-    uint8_t* const mc = (patch && p.masked_chars) ? p.masked_chars + j * p.row_pitch : nullptr;
-    uint8_t* const ms = (patch && p.masked_substr_ids) ? p.masked_substr_ids + j * p.row_pitch : nullptr;
-    uint8_t* const cb = (!patch && p.compact_bytes) ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
+                                                  uint32_t n_rec, uint32_t n_cmp) {
+    uint8_t* const mc = p.masked_chars ? p.masked_chars + j * p.row_pitch : nullptr;
+    uint8_t* const ms = p.masked_substr_ids ? p.masked_substr_ids + j * p.row_pitch : nullptr;
+    uint8_t* const cb = p.compact_bytes ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
     auto record = [&](uint32_t start, uint32_t len, uint32_t sid, uint32_t coff) {
-        if (!patch && p.records && n_rec < p.max_records) {
+        if (p.records && n_rec < p.max_records) {
             b2r_substr_record r; r.start = start; r.len = len; r.substr_id = sid; r.compact_off = coff;
             p.records[j * p.max_records + n_rec] = r;
         }
@@ -146,9 +146,23 @@ struct Granule {
     uint32_t n;                    // rows that are characters (1..16)
 
     // granule g of string j (src = its first byte, L its length); 16*g < L
-    __device__ __forceinline__ void load(const WalkParams& p, uint64_t j, const uint8_t* src, uint32_t L, uint32_t g) {
+    // stash_g / stash_s: a granule of this string kept in shared memory by the walk (fused mode): vector v at stash_s + 512*v,
+    // v = 0 the bytes, then the states of every def
+    __device__ __forceinline__ void load(const WalkParams& p, uint64_t j, const uint8_t* src, uint32_t L, uint32_t g, uint32_t stash_g, uint32_t stash_s) {
         const uint32_t base = 16 * g;
         n = L - base < 16 ? L - base : 16;
+        if (g == stash_g) {
+            auto lds = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
+            const uint4 b = lds(stash_s);
+            w[0] = b.x; w[1] = b.y; w[2] = b.z; w[3] = b.w;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const uint4 a = lds(stash_s + (1 + d * sizeof(ST)) * 512);
+                sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
+                if (sizeof(ST) == 2) { const uint4 b2 = lds(stash_s + (2 + d * sizeof(ST)) * 512); sv[d][4 * (sizeof(ST) - 1)] = b2.x; sv[d][4 * (sizeof(ST) - 1) + 1] = b2.y; sv[d][4 * (sizeof(ST) - 1) + 2] = b2.z; sv[d][4 * (sizeof(ST) - 1) + 3] = b2.w; }
+            }
+            return;
+        }
         // 16 bytes from an arbitrary address: two aligned 16-byte loads shifted into place; the second one is only
         // touched when the bytes needed reach into it
         const uintptr_t addr = reinterpret_cast<uintptr_t>(src + base);
@@ -203,6 +217,7 @@ struct LaneString {
     uint64_t j;
     const uint8_t* src;
     uint32_t L;
+    uint32_t stash_g, stash_s;  // granule kept in shared memory by the walk (fused mode), NO_POS = none
     // results of the scan
     uint32_t seg_a[EMIT_NSEG], seg_b[EMIT_NSEG], n_seg;   // masked segments [a,b), in order; n_seg may exceed EMIT_NSEG
     uint32_t n_rec, n_cmp;
@@ -215,19 +230,26 @@ struct LaneString {
     uint32_t bw_t, sw[D], ew[D]; // bitmap words being assembled: rows [32*bw_t, 32*bw_t+32)
 
     __device__ __forceinline__ LaneString(const WalkParams& p_, const EmitTables<D>& tb_, uint64_t j_, const uint8_t* src_, uint32_t L_)
-        : p(p_), tb(tb_), j(j_), src(src_), L(L_) {}
+        : p(p_), tb(tb_), j(j_), src(src_), L(L_), stash_g(NO_POS), stash_s(0) {}
 
     __device__ __forceinline__ uint32_t entry(int d, uint32_t c, uint32_t s) const {
         const uint32_t S = p.def[d].num_states;
         return s < S ? tb.trans[d][(uint32_t)tb.cls[d][c] * S + s] : ENT_INVALID;   // state S = the trap state of the walk
     }
+    // can a transition out of state s carry a substr id (or is s the trap state)?  One bit per state, packed by defs.cpp.
+    __device__ __forceinline__ bool state_is_hot(int d, uint32_t s) const {
+        if (s >= 64u) return true;
+        const uint32_t m = s < 32u ? p.def[d].hot_states[0] : p.def[d].hot_states[1];
+        return (m >> (s & 31u)) & 1u;
+    }
 
     // ---- scan ----------------------------------------------------------------------------------------------------------
+    // PATCH: the string has more masked segments than the registers hold; this second scan only emits them one by one
     template <bool PATCH>
     __device__ __forceinline__ void boundary(uint32_t pos, bool b_is, bool b_ie) {
         if (prev_valid && prev_is && b_ie) {                             // [prev_pos, pos) is masked
-            if (!PATCH || n_seg >= EMIT_NSEG) {
-                const uint2 r = emit_segment<D, ST>(p, tb, j, src, prev_pos, pos, n_rec, n_cmp, PATCH);
+            if (PATCH) {
+                const uint2 r = emit_segment<D, ST>(p, tb, j, src, prev_pos, pos, n_rec, n_cmp);
                 n_rec = r.x; n_cmp = r.y;
             }
 #pragma unroll
@@ -247,38 +269,6 @@ struct LaneString {
         }
         next_row = NO_POS; carry_s = 0; carry_ie = 0;
     }
-    // row i < L with byte c and states s[]; rows whose id sum is 0 in every def may be skipped
-    template <bool PATCH>
-    __device__ __forceinline__ void row(uint32_t i, uint32_t c, const uint32_t* s) {
-        if (next_row != i) close_gap<PATCH>();
-        uint32_t sum = 0, is_sum = 0, ie_next = 0;
-#pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint32_t S = p.def[d].num_states;
-            const uint32_t e = entry(d, c, s[d]);
-            if (e & ENT_INVALID) { invalid = true; continue; }
-            const uint32_t sid = ent_sid(e);
-            if (!sid) continue;
-            sum += sid;
-            if (e & ENT_IS_START) {                                      // endpoint lookup src/lib.rs:235-258
-                is_sum++;
-                if (!PATCH) {
-                    const uint32_t bin = (sid - p.def[d].sid_offset) * S + s[d];
-                    if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + bin, 1u); else atomicAdd(p.def[d].ep_start + bin, 1ull);
-                }
-            }
-            if (e & ENT_IS_END) {                                        // endpoint lookup src/lib.rs:260-284
-                ie_next++;
-                if (!PATCH) {
-                    const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e & ENT_NEXT_MASK);
-                    if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + p.def[d].num_substrs * S + bin, 1u); else atomicAdd(p.def[d].ep_end + bin, 1ull);
-                }
-            }
-        }
-        if (is_sum > 1 || carry_ie > 1) overlap = true;
-        if (sum != carry_s && (is_sum | carry_ie)) boundary<PATCH>(i, is_sum != 0, carry_ie != 0);
-        carry_s = sum; carry_ie = ie_next; next_row = i + 1;
-    }
     __device__ __forceinline__ void flush_bitmap_words() {
         if (bw_t == NO_POS) return;
 #pragma unroll
@@ -292,25 +282,64 @@ struct LaneString {
     template <bool PATCH>
     __device__ __forceinline__ void scan_granule(uint32_t g, bool partner_flagged) {
         Granule<D, ST> gr;
-        gr.load(p, j, src, L, g);
-        // pass 1, unrolled, all lanes in step: substr ids and flags of the 16 rows; which rows need the boundary logic?
-        uint32_t hot = 0, sidv[D][4], sb[D], eb[D];
-#pragma unroll
-        for (int d = 0; d < D; d++) { sb[d] = 0; eb[d] = 0; sidv[d][0] = sidv[d][1] = sidv[d][2] = sidv[d][3] = 0; }
+        gr.load(p, j, src, L, g, stash_g, stash_s);
+        // pass 1, unrolled, all lanes in step: rows whose state can start a transition with a substr id (or is the trap state)
+        uint32_t hot = 0;
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const uint32_t c = gr.byte_at(r);
+#pragma unroll
+            for (int d = 0; d < D; d++)
+                if (state_is_hot(d, gr.state_at(d, r))) hot |= 1u << r;
+        }
+        hot &= (1u << gr.n) - 1u;                                        // rows past the end of the string are not characters
+        // pass 2, one loop body shared by all lanes: each lane handles ITS next candidate row
+        uint32_t sidv[D][4];
+#pragma unroll
+        for (int d = 0; d < D; d++) sidv[d][0] = sidv[d][1] = sidv[d][2] = sidv[d][3] = 0;
+        if (!PATCH && (g >> 1) != bw_t) { flush_bitmap_words(); bw_t = g >> 1; }
+        while (hot) {
+            const uint32_t r = (uint32_t)__ffs((int)hot) - 1u;
+            hot &= hot - 1;
+            const uint32_t i = 16 * g + r;
+            const uint32_t c = gr.byte_dyn(r);
+            uint32_t sum = 0, is_sum = 0, ie_next = 0;
+            bool any = false;
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                uint32_t e = entry(d, c, gr.state_at(d, r));
-                if ((uint32_t)r >= gr.n) e = 0;                          // rows past the end of the string are not characters
-                if (e & (ENT_SID_MASK | ENT_INVALID)) hot |= 1u << r;
+                const uint32_t S = p.def[d].num_states;
+                const uint32_t st = gr.state_dyn(d, r);
+                const uint32_t e = entry(d, c, st);
+                if (e & ENT_INVALID) { invalid = true; continue; }
+                const uint32_t sid = ent_sid(e);
+                if (!sid) continue;
+                any = true;
+                sum += sid;
                 if (!PATCH) {
-                    sidv[d][r >> 2] |= ent_sid(e) << (8 * (r & 3));
-                    sb[d] |= ((e >> 24) & 1u) << r;
-                    eb[d] |= ((e >> 25) & 1u) << r;
+                    const uint32_t v = sid << (8 * (r & 3));
+                    if ((r >> 2) == 0) sidv[d][0] |= v; else if ((r >> 2) == 1) sidv[d][1] |= v; else if ((r >> 2) == 2) sidv[d][2] |= v; else sidv[d][3] |= v;
+                }
+                if (e & ENT_IS_START) {                                  // start_enable; endpoint lookup src/lib.rs:235-258
+                    is_sum++;
+                    if (!PATCH) {
+                        sw[d] |= 1u << (i & 31);
+                        const uint32_t bin = (sid - p.def[d].sid_offset) * S + st;
+                        if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + bin, 1u); else atomicAdd(p.def[d].ep_start + bin, 1ull);
+                    }
+                }
+                if (e & ENT_IS_END) {                                    // end_enable; endpoint lookup src/lib.rs:260-284
+                    ie_next++;
+                    if (!PATCH) {
+                        ew[d] |= 1u << (i & 31);
+                        const uint32_t bin = (sid - p.def[d].sid_offset) * S + (e & ENT_NEXT_MASK);
+                        if (tb.ep_s[d]) atomicAdd(tb.ep_s[d] + p.def[d].num_substrs * S + bin, 1u); else atomicAdd(p.def[d].ep_end + bin, 1ull);
+                    }
                 }
             }
+            if (!any) continue;                                          // id sum 0 in every def: like a row of an unflagged granule
+            if (next_row != i) close_gap<PATCH>();
+            if (is_sum > 1 || carry_ie > 1) overlap = true;
+            if (sum != carry_s && (is_sum | carry_ie)) boundary<PATCH>(i, is_sum != 0, carry_ie != 0);
+            carry_s = sum; carry_ie = ie_next; next_row = i + 1;
         }
         if (!PATCH) {
             // the complete sector of the substr-id columns: my 16 bytes, and zeros for the partner unless it writes itself
@@ -323,18 +352,6 @@ struct LaneString {
                 *reinterpret_cast<uint4*>(row + base) = make_uint4(sidv[d][0], sidv[d][1], sidv[d][2], sidv[d][3]);
                 if (partner) *reinterpret_cast<uint4*>(row + pbase) = make_uint4(0, 0, 0, 0);
             }
-            if ((g >> 1) != bw_t) { flush_bitmap_words(); bw_t = g >> 1; }
-#pragma unroll
-            for (int d = 0; d < D; d++) { sw[d] |= sb[d] << (16 * (g & 1)); ew[d] |= eb[d] << (16 * (g & 1)); }
-        }
-        // pass 2, one loop body shared by all lanes: each lane handles ITS next hot row
-        while (hot) {
-            const uint32_t r = (uint32_t)__ffs((int)hot) - 1u;
-            hot &= hot - 1;
-            uint32_t st[D];
-#pragma unroll
-            for (int d = 0; d < D; d++) st[d] = gr.state_dyn(d, r);
-            row<PATCH>(16 * g + r, gr.byte_dyn(r), st);
         }
     }
     // fw0 / fw1: granule flags 0..63 of this string; further words come from the flag buffer `flags`
@@ -359,48 +376,71 @@ struct LaneString {
     }
 
     // ---- masks ---------------------------------------------------------------------------------------------------------
-    // bit r set: row 16g + r lies inside one of the first EMIT_NSEG masked segments
-    __device__ __forceinline__ uint32_t masked_rows(uint32_t g) const {
-        const uint32_t base = 16 * g;
-        uint32_t m = 0;
+    // The masked segments (at most EMIT_NSEG, in order): the complete sectors of masked_chars / masked_substr_ids they
+    // touch, the compact bytes, and one record per maximal run of a constant id sum (src/lib.rs:740-764).
+    __device__ __forceinline__ void write_masks() {
+        uint8_t* const mc = p.masked_chars ? p.masked_chars + j * p.row_pitch : nullptr;
+        uint8_t* const ms = p.masked_substr_ids ? p.masked_substr_ids + j * p.row_pitch : nullptr;
+        uint8_t* const cb = p.compact_bytes ? p.compact_bytes + j * (uint64_t)p.compact_pitch : nullptr;
+        uint32_t cur_t = NO_POS;                                         // window being assembled
+        uint32_t mcv[8], msv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { mcv[k] = 0; msv[k] = 0; }
+        auto flush = [&]() {
+            if (cur_t == NO_POS) return;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint64_t o = 32ull * cur_t + 16ull * h;
+                if (o + 16 > p.row_pitch) continue;                      // the last window of a row can be half
+                if (mc) *reinterpret_cast<uint4*>(mc + o) = make_uint4(mcv[4 * h], mcv[4 * h + 1], mcv[4 * h + 2], mcv[4 * h + 3]);
+                if (ms) *reinterpret_cast<uint4*>(ms + o) = make_uint4(msv[4 * h], msv[4 * h + 1], msv[4 * h + 2], msv[4 * h + 3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { mcv[k] = 0; msv[k] = 0; }
+        };
+        uint32_t run_start = 0, run_sum = 0, run_coff = 0;
+        bool in_run = false;
+        auto close_run = [&](uint32_t end) {
+            if (!in_run) return;
+            if (p.records && n_rec < p.max_records) {
+                b2r_substr_record r; r.start = run_start; r.len = end - run_start; r.substr_id = run_sum; r.compact_off = run_coff;
+                p.records[j * p.max_records + n_rec] = r;
+            }
+            n_rec++; in_run = false;
+        };
 #pragma unroll
         for (int k = 0; k < EMIT_NSEG; k++) {
-            if ((uint32_t)k < n_seg && seg_b[k] > base && seg_a[k] < base + 16) {
-                const uint32_t lo = seg_a[k] > base ? seg_a[k] - base : 0u;
-                const uint32_t hi = seg_b[k] < base + 16 ? seg_b[k] - base : 16u;
-                m |= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-            }
-        }
-        return m;
-    }
-    // window t = rows [32t, 32t+32), reached by a masked segment: the complete sector of masked_chars / masked_substr_ids
-    __device__ __forceinline__ void write_masked_window(uint32_t t) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const uint32_t g = 2 * t + h;
-            const uint32_t base = 16 * g;
-            if ((uint64_t)base + 16 > p.row_pitch) continue;             // past the row (the last window of a row can be half)
-            uint32_t mcv[4] = {0, 0, 0, 0}, msv[4] = {0, 0, 0, 0};
-            const uint32_t mrows = base < L ? masked_rows(g) : 0u;
-            if (mrows) {
+            if ((uint32_t)k >= n_seg) continue;
+            const uint32_t a = seg_a[k], b = seg_b[k];
+            for (uint32_t g = a >> 4; g <= (b - 1) >> 4; g++) {
+                if ((g >> 1) != cur_t) { flush(); cur_t = g >> 1; }
                 Granule<D, ST> gr;
-                gr.load(p, j, src, L, g);
-#pragma unroll
-                for (int r = 0; r < 16; r++) {
-                    const uint32_t c = gr.byte_at(r);
+                gr.load(p, j, src, L, g, stash_g, stash_s);
+                const uint32_t lo = a > 16 * g ? a - 16 * g : 0u, hi = b < 16 * g + 16 ? b - 16 * g : 16u;
+                for (uint32_t r = lo; r < hi; r++) {
+                    const uint32_t i = 16 * g + r;
+                    const uint32_t c = gr.byte_dyn(r);
                     uint32_t sum = 0;
 #pragma unroll
                     for (int d = 0; d < D; d++) {
-                        const uint32_t e = entry(d, c, gr.state_at(d, r));
+                        const uint32_t e = entry(d, c, gr.state_dyn(d, r));
                         sum += (e & ENT_INVALID) ? 0u : ent_sid(e);
                     }
-                    if ((mrows >> r) & 1u) { mcv[r >> 2] |= c << (8 * (r & 3)); msv[r >> 2] |= sum << (8 * (r & 3)); }
+                    const uint32_t q = (i >> 2) & 7u, sh = 8 * (i & 3u);
+#pragma unroll
+                    for (int w = 0; w < 8; w++)
+                        if (q == (uint32_t)w) { mcv[w] |= c << sh; msv[w] |= sum << sh; }
+                    if (cb && n_cmp < p.compact_pitch) cb[n_cmp] = (uint8_t)c;
+                    if (!in_run || sum != run_sum || i == a) {          // a new segment always starts a new run (the id sum changes at a boundary)
+                        close_run(i);
+                        in_run = true; run_start = i; run_sum = sum; run_coff = n_cmp;
+                    }
+                    n_cmp++;
                 }
             }
-            const uint64_t o = j * p.row_pitch + base;
-            if (p.masked_chars) *reinterpret_cast<uint4*>(p.masked_chars + o) = make_uint4(mcv[0], mcv[1], mcv[2], mcv[3]);
-            if (p.masked_substr_ids) *reinterpret_cast<uint4*>(p.masked_substr_ids + o) = make_uint4(msv[0], msv[1], msv[2], msv[3]);
+            close_run(b);
         }
+        flush();
     }
 };
 
@@ -416,7 +456,7 @@ struct TileEmitter {
     // Lane = string.  off / Ll / live: the lane's string (live = in range and not too long); fw0 / fw1: its granule flags
     // 0..63 (further words are read from p.fmask); fin[]: its final states; filled: the caller has zeroed the tile's rows.
     __device__ __forceinline__ void run_tile(uint64_t tile_base, bool valid, bool live, uint64_t off, uint32_t Ll, uint32_t fw0, uint32_t fw1,
-                                             const uint32_t* fin, EmitTotals& tot, bool filled) {
+                                             const uint32_t* fin, EmitTotals& tot, bool filled, uint32_t stash_g = NO_POS, uint32_t stash_s = 0) {
         constexpr uint32_t FULL = 0xffffffffu;
         const uint64_t N = p.n_strings;
         const uint32_t M = p.max_chars;
@@ -441,29 +481,23 @@ struct TileEmitter {
         uint32_t r_nrec = 0, r_ncmp = 0, r_flags = 0;
         bool patch = false;
         LaneString<D, ST> ls(p, tb, jl, p.bytes + off, Ll);
+        ls.stash_g = stash_g; ls.stash_s = stash_s;
         if (live && !(p.debug & 2) && (p.fm_words > 2 || (fw0 | fw1) != 0)) {
             ls.template scan<false>(fw0, fw1, p.fmask);
             if (ls.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
             else {
-                r_nrec = ls.n_rec; r_ncmp = ls.n_cmp;
                 if (ls.overlap) r_flags = B2R_ST_OVERLAP;
                 patch = ls.n_seg > EMIT_NSEG;
-                uint32_t last_t = NO_POS;
-#pragma unroll
-                for (int k = 0; k < EMIT_NSEG; k++) {
-                    if ((uint32_t)k >= ls.n_seg) continue;
-                    for (uint32_t t = ls.seg_a[k] >> 5; t <= (ls.seg_b[k] - 1) >> 5; t++) {
-                        if (t == last_t) continue;                       // written with the previous segment (all segments of a window go together)
-                        last_t = t;
-                        ls.write_masked_window(t);
-                    }
-                }
+                if (!patch) { ls.write_masks(); r_nrec = ls.n_rec; r_ncmp = ls.n_cmp; }
             }
         }
-        // ---- more masked segments than the registers hold: patch their rows byte by byte (rare) ------------------------------
+#pragma unroll
+        for (int d = 0; d < D; d++)
+            if (live && fin[d] >= p.def[d].num_states) r_flags = B2R_ST_INVALID_TRANSITION;   // the last character had no transition
+        // ---- more masked segments than the registers hold: emit them one by one, byte by byte (rare) --------------------------
         if (__any_sync(FULL, patch)) {
             __syncwarp();
-            if (patch) ls.template scan<true>(fw0, fw1, p.fmask);
+            if (patch) { ls.template scan<true>(fw0, fw1, p.fmask); r_nrec = ls.n_rec; r_ncmp = ls.n_cmp; }
         }
 
         // ---- accept rule (src/lib.rs:427-457), status records (lane = string) --------------------------------------------

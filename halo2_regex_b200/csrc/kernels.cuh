@@ -24,6 +24,7 @@ struct DefDev {
     uint32_t accepted_state;
     uint32_t sid_offset;
     uint32_t num_substrs;
+    uint32_t hot_states[2];          // bit s: some transition out of state s (< 64) carries a substr id (emit.cuh prefilter)
     unsigned long long* hist;        // dense [256][S] multiplicity bins (global, u64)
     unsigned long long* ep_start;    // [num_substrs][S] start-endpoint counters
     unsigned long long* ep_end;      // [num_substrs][S]

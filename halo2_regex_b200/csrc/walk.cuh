@@ -84,7 +84,7 @@ struct WalkLayout {
     uint32_t emit;                 // emit tables + endpoint counters (emit.cuh), fused mode
     uint32_t zero;                 // WALK_ZERO_BYTES of zeros, fused mode
     uint32_t tiles;                // first per-warp tile
-    uint32_t per_warp;
+    uint32_t per_warp, st_off, stash_off;   // bytes per warp; offsets of the state tile / granule stash inside
     uint32_t align;                // alignment the base needs (the largest table row)
 };
 __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t state_bytes) {
@@ -112,7 +112,12 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
     L.zero = cur;
     if (p.fuse) cur += WALK_ZERO_BYTES;
     L.tiles = cur;
-    L.per_warp = 2 * 32 * WALK_PITCH + p.n_defs * 32 * (WALK_DCH * state_bytes + 16);
+    // per warp: two input tiles (double buffer); a state tile per def — except for one def with 1-byte states, whose states
+    // overwrite the consumed bytes of the current input tile; the stash of one flagged granule per lane (fused emit stage)
+    const bool inplace = p.n_defs == 1 && state_bytes == 1;
+    L.st_off = 2 * 32 * WALK_PITCH;
+    L.stash_off = L.st_off + (inplace ? 0u : p.n_defs * 32 * (WALK_DCH * state_bytes + 16));
+    L.per_warp = L.stash_off + (p.fuse ? 32u * 16u * (1u + p.n_defs * state_bytes) : 0u);
     L.align = al;
     return L;
 }
@@ -194,7 +199,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         hist_s[d] = base_s + lay.hist[d];
     }
     const uint32_t in_s = base_s + lay.tiles + (uint32_t)warp * lay.per_warp;
-    const uint32_t st_s = in_s + 2 * 32 * PITCH;
+    constexpr bool INPLACE = D == 1 && SB == 1;                         // states overwrite the consumed input bytes
+    const uint32_t st_s = in_s + lay.st_off;
+    const uint32_t stash_s = in_s + lay.stash_off + lane * 16;         // vector v of my stash at stash_s + v*512
     const int kv = lane % VPR, r0 = lane / VPR;                         // input staging: vector kv of rows r0 + (32/VPR)*i
     const int skv = lane % VPS, sr0 = lane / VPS;                       // state store:   vector skv of rows sr0 + (32/VPS)*i
 
@@ -295,6 +302,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         }
 
         uint32_t fm = 0, fw0 = 0, fw1 = 0;                              // granule flags: current group of 32 granules, words 0 and 1
+        uint32_t stash_g = NO_POS;                                      // granule kept in my stash
 #pragma unroll 1
         for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
             const uint32_t cbase = chunk * DCH;
@@ -382,12 +390,23 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 }
 #pragma unroll
                 for (int d = 0; d < D; d++) {
-                    const uint32_t a = st_s + (d * 32 + lane) * SPITCH + g * 16 * SB;
+                    const uint32_t a = INPLACE ? my_in + g * 16 : st_s + (d * 32 + lane) * SPITCH + g * 16 * SB;
                     sts128(a, pk[d][0], pk[d][1], pk[d][2], pk[d][3]);
-                    if (SB == 2) sts128(a + 16, pk[d][4], pk[d][5], pk[d][6], pk[d][7]);
+                    if (SB == 2) sts128(a + 16, pk[d][4 * (SB - 1)], pk[d][4 * (SB - 1) + 1], pk[d][4 * (SB - 1) + 2], pk[d][4 * (SB - 1) + 3]);
                 }
                 const uint32_t gi = (cbase >> 4) + g;                   // granule index
-                if (acc & 1u) fm |= 1u << (gi & 31);
+                if (acc & 1u) {
+                    fm |= 1u << (gi & 31);
+                    if (p.fuse && stash_g == NO_POS) {                  // keep the first flagged granule of my string for the emit stage
+                        stash_g = gi;
+                        sts128(stash_s, w[0], w[1], w[2], w[3]);
+#pragma unroll
+                        for (int d = 0; d < D; d++) {
+                            sts128(stash_s + (1 + d * SB) * 512, pk[d][0], pk[d][1], pk[d][2], pk[d][3]);
+                            if (SB == 2) sts128(stash_s + (2 + d * SB) * 512, pk[d][4 * (SB - 1)], pk[d][4 * (SB - 1) + 1], pk[d][4 * (SB - 1) + 2], pk[d][4 * (SB - 1) + 3]);
+                        }
+                    }
+                }
             }
             __syncwarp();
 
@@ -400,7 +419,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                     const int row = sr0 + (32 / VPS) * i;
                     const uint32_t elem = cbase + (uint32_t)skv * (16 / SB);   // first row-element of this vector
                     if (row < (int)rows_here && elem < Mpad) {
-                        const uint4 v = lds128(st_s + (d * 32 + row) * SPITCH + skv * 16);
+                        const uint4 v = lds128(INPLACE ? in_s + (chunk & 1) * (32 * PITCH) + row * PITCH + skv * 16 : st_s + (d * 32 + row) * SPITCH + skv * 16);
                         *reinterpret_cast<uint4*>(col + ((tile_base + row) * rp + elem) * SB) = v;
                     }
                 }
@@ -422,7 +441,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             uint32_t fin[D];
 #pragma unroll
             for (int d = 0; d < D; d++) fin[d] = cur[d] >> 16;
-            emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true);
+            emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true, stash_g, stash_s);
         }
     }
     if (p.fuse) emit_publish<D>(p, etb, tot);
