@@ -126,7 +126,7 @@ __host__ __device__ inline size_t walk_smem_bytes(const WalkParams& p, uint32_t 
     return (size_t)L.align + L.tiles + (size_t)warps * L.per_warp;   // + align: the dynamic base is only 16-byte aligned
 }
 
-// TM: TABLE_REPL (also runs TABLE_PLAIN: the stride is a run-time value) or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
+// TM: TABLE_REPL, TABLE_PLAIN or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
 template <int D, typename ST, int TM, int HM>
 __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_constant__ WalkParams p) {
     constexpr int DCH = WALK_DCH, PITCH = WALK_PITCH;
@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 
     const WalkLayout lay = walk_layout(p, SB);
     const uint32_t base_s = (smem_u32(dsmem) + lay.align - 1) & ~(lay.align - 1);
-    const uint32_t stride = SMEM_TAB ? walk_stride(p.table_mode) : 0u;
-    const uint32_t laneoff = (SMEM_TAB && p.table_mode == TABLE_REPL) ? (uint32_t)lane * 4u : 0u;
+    constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_PLAIN ? 4u : 0u;
+    const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : 0u;
 
     // ---- stage the tables ----------------------------------------------------------------------------------------------
     if (SMEM_TAB) {
-        const uint32_t csh = p.table_mode == TABLE_REPL ? 5u : 0u;   // log2(copies)
+        constexpr uint32_t csh = TM == (int)TABLE_REPL ? 5u : 0u;   // log2(copies)
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t n = p.def[d].num_classes * p.def[d].padded_states;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                     // ---- hot path: 16 real characters, no data-dependent branch ---------------------------------------
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        uint32_t held[D];                               // u16 states: entry of the even position
+                        uint32_t before[D][4];                          // the entry that led to the state of row 4q + j
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t c = prmt(w[q], 0u, 0x4440u + j);
@@ -340,16 +340,23 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
                             for (int d = 0; d < D; d++) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);
-                                count(d, cur[d], c);
-                                if (SB == 1) {                          // state byte (cur byte 2) into byte j of the pack
-                                    const uint32_t sel = j == 0 ? 0x3216u : j == 1 ? 0x3260u : j == 2 ? 0x3610u : 0x6210u;
-                                    pk[d][q] = prmt(j == 0 ? 0u : pk[d][q], cur[d], sel);
-                                } else {
-                                    if ((j & 1) == 0) held[d] = cur[d];
-                                    else pk[d][q * 2 + (j >> 1)] = prmt(held[d], cur[d], 0x7632u);
-                                }
-                                acc |= e;
+                                if (HM == (int)HIST_SMEM && SB == 1)     // bin index (state << 8 | byte) in one byte permute
+                                    red_shared_inc(hist_s[d] + prmt(cur[d], w[q], 0x3324u + j) * 4);
+                                else count(d, cur[d], c);
+                                before[d][j] = cur[d];
                                 cur[d] = e;
+                            }
+                        }
+#pragma unroll
+                        for (int d = 0; d < D; d++) {
+                            acc |= before[d][1] | before[d][2];           // entries of rows 4q, 4q+1 (3-input LOP3s)
+                            acc |= before[d][3] | cur[d];                 // rows 4q+2, 4q+3
+                            if (SB == 1) {                                // state bytes (entry byte 2) of four rows into one word
+                                const uint32_t lo = prmt(before[d][0], before[d][1], 0x4462u), hi = prmt(before[d][2], before[d][3], 0x4462u);
+                                pk[d][q] = prmt(lo, hi, 0x5410u);
+                            } else {
+                                pk[d][q * 2] = prmt(before[d][0], before[d][1], 0x7632u);
+                                pk[d][q * 2 + 1] = prmt(before[d][2], before[d][3], 0x7632u);
                             }
                         }
                     }
