@@ -13,6 +13,7 @@
 #include "../../include/b2r.h"
 #include "defs.hpp"
 #include "kernels.cuh"
+#include "long.cuh"
 
 using namespace b2r;
 
@@ -67,6 +68,7 @@ struct b2r_config {
     int force_table_mode = -1;        // testing hooks: B2R_TABLE_MODE=repl|plain|global, B2R_HIST_MODE=smem|global
     int force_hist_mode = -1;
     DevBuf ws_fmask;                  // granule flags (walk -> emit)
+    DevBuf ws_long;                   // long-string path: chunk offsets, transition-vector tree, entry states, flag summary
     DevBuf ws_states[B2R_MAX_DEFS];   // state column of a def the caller did not ask for (emit reads it)
     WalkParams last = {};
     bool have_last = false;
@@ -147,8 +149,8 @@ int upload_tables(b2r_config* c) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int check_outputs(const b2r_config* c, const b2r_outputs* o, bool check_ptrs) {
-    const uint64_t M = c->max_chars;
+int check_outputs(const b2r_config* c, const b2r_outputs* o, bool check_ptrs, uint64_t M = 0) {
+    if (!M) M = c->max_chars;
     if (o->row_pitch < M || o->row_pitch % 16) { set_error("row_pitch %llu must be >= max_chars_size and a multiple of 16", (unsigned long long)o->row_pitch); return B2R_ERR_ALIGNMENT; }
     if (o->bitmap_pitch < (M + 7) / 8 || o->bitmap_pitch % 4) { set_error("bitmap_pitch %llu must be >= ceil(M/8) and a multiple of 4", (unsigned long long)o->bitmap_pitch); return B2R_ERR_ALIGNMENT; }
     if (!check_ptrs) return B2R_OK;
@@ -351,7 +353,7 @@ void b2r_config_free(b2r_config* c) {
     if (c->device >= 0) {
         DeviceGuard g(c->device);
         cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
-        c->ws_fmask.release();
+        c->ws_fmask.release(); c->ws_long.release();
         for (auto& b : c->ws_states) b.release();
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
@@ -564,10 +566,94 @@ int b2r_match_substrs(b2r_config* c, const uint8_t* characters, uint64_t len, co
     return b2r_match_batch_host(c, characters, offsets, 1, h_out, result);
 }
 
-int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2r_outputs* d_out, void* cuda_stream) {
-    (void)c; (void)d_bytes; (void)len; (void)d_out; (void)cuda_stream;
-    set_error("b2r_match_long: the chunked parallel-prefix path is not built yet");
-    return B2R_ERR_UNSUPPORTED;
+int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2r_outputs* o, void* cuda_stream) {
+    if (!c || !o || (!d_bytes && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
+    if (len + 1 > 0xFFFFFFF0ull) { set_error("string of %llu bytes: at most 2^32 - 17 rows are supported", (unsigned long long)len); return B2R_ERR_UNSUPPORTED; }
+    if (!aligned16(d_bytes)) { set_error("bytes must be 16-byte aligned"); return B2R_ERR_ALIGNMENT; }
+    const uint64_t M = len + 1;
+    int rc = check_outputs(c, o, true, M);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    bool wide = false;
+    for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
+    for (uint32_t d = 0; d < c->n_defs; d++)
+        if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
+    c->last_launches = 0;
+    CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none
+
+    // ---- workspace: chunk offsets (+ the {0, len} pair of the whole string), flag words, summary, tree of transition vectors
+    const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (len + LONG_CHUNK - 1) / LONG_CHUNK);
+    const uint32_t chunk_fm_words = (LONG_CHUNK / 16 + 31) / 32;
+    const size_t nodes = long_level_nodes(n_chunks);
+    size_t need = 0;
+    auto slot = [&](size_t bytes) { size_t off = need; need += align_up(bytes, 256); return off; };
+    const size_t off_offsets = slot((size_t)(n_chunks + 3) * 8), off_fmask = slot((size_t)chunk_fm_words * n_chunks * 4), off_summary = slot((size_t)((n_chunks + 31) / 32) * 4);
+    size_t off_maps[B2R_MAX_DEFS], off_entry[B2R_MAX_DEFS], off_states[B2R_MAX_DEFS];
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        off_maps[d] = slot(nodes * (c->packed[d].num_states + 1) * 2);
+        off_entry[d] = slot(nodes * 2);
+        off_states[d] = o->states[d] ? 0 : slot(align_up(M, 16) * (wide ? 2 : 1) + 64);
+    }
+    if ((rc = c->ws_long.reserve(need))) return rc;
+    unsigned char* ws = (unsigned char*)c->ws_long.p;
+    uint64_t* d_offsets = (uint64_t*)(ws + off_offsets);
+    const uint64_t whole[2] = {0, len};
+    CUDA_TRY(cudaMemcpyAsync(d_offsets + n_chunks + 1, whole, sizeof whole, cudaMemcpyHostToDevice, st));
+
+    // ---- 1 + 2: transition vectors of the chunks, composition tree, entry state of every chunk ------------------------------
+    LongParams lp;
+    memset(&lp, 0, sizeof lp);
+    lp.bytes = d_bytes; lp.len = len; lp.n_chunks = n_chunks; lp.n_defs = c->n_defs; lp.offsets = d_offsets;
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        lp.def[d].byte_class = c->dev[d].byte_class; lp.def[d].trans = c->dev[d].trans;
+        lp.def[d].num_states = c->packed[d].num_states; lp.def[d].first_state = c->packed[d].first_state;
+        lp.def[d].maps = (uint16_t*)(ws + off_maps[d]); lp.def[d].entry = (uint16_t*)(ws + off_entry[d]);
+    }
+    if ((rc = launch_long_prepare(lp, st, &c->last_launches))) return rc;
+
+    // ---- 3: the walk, chunk = string, one contiguous state row ------------------------------------------------------------
+    b2r_outputs seg = *o;
+    seg.row_pitch = LONG_CHUNK;
+    WalkParams pw;
+    fill_walk_params(c, pw, d_bytes, d_offsets, n_chunks, len, &seg, LONG_CHUNK + 1);
+    pw.fuse = 0; pw.prefilled = 0; pw.segment_mode = 1;
+    pw.fmask = (uint32_t*)(ws + off_fmask);
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        if (!pw.def[d].states) pw.def[d].states = ws + off_states[d];
+        pw.def[d].init_states = lp.def[d].entry;                          // level 0 of the tree
+    }
+    if ((rc = plan_walk(pw, wide, c->force_table_mode, c->force_hist_mode))) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
+    if ((rc = launch_walk(pw, wide, st, nullptr))) return rc;
+    c->last_launches++;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
+
+    // ---- 4: zero the sparse columns, then the ordered emit stage of the one string ---------------------------------------------
+    auto zero = [&](void* ptr, size_t bytes) { return ptr ? cudaMemsetAsync(ptr, 0, bytes, st) : cudaSuccess; };
+    const size_t col_bytes = align_up(M, 16), bm_bytes = align_up((M + 7) / 8, 4);
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        CUDA_TRY(zero(o->substr_ids[d], col_bytes));
+        CUDA_TRY(zero(o->start_enable[d], bm_bytes));
+        CUDA_TRY(zero(o->end_enable[d], bm_bytes));
+    }
+    CUDA_TRY(zero(o->masked_chars, col_bytes));
+    CUDA_TRY(zero(o->masked_substr_ids, col_bytes));
+    WalkParams& pe = c->last;
+    fill_walk_params(c, pe, d_bytes, d_offsets + n_chunks + 1, 1, len, o, M);
+    pe.fuse = 0; pe.prefilled = 1;
+    pe.fmask = pw.fmask;
+    for (uint32_t d = 0; d < c->n_defs; d++) pe.def[d].states = pw.def[d].states;
+    c->have_last = true;
+    if ((rc = launch_long_emit(pe, wide, pw.fmask, (uint32_t*)(ws + off_summary), n_chunks, chunk_fm_words, st, &c->last_launches))) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    rc = enqueue_finalize(c, o, 1, M, st);
+    if (rc) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], st));
+    return B2R_OK;
 }
 
 uint32_t b2r_last_launch_count(const b2r_config* c) { return c ? c->last_launches : 0; }

@@ -354,15 +354,22 @@ struct LaneString {
             }
         }
     }
-    // fw0 / fw1: granule flags 0..63 of this string; further words come from the flag buffer `flags`
-    template <bool PATCH>
-    __device__ __forceinline__ void scan(uint32_t fw0, uint32_t fw1, const uint32_t* flags) {
+    __device__ __forceinline__ void scan_begin() {
         n_seg = 0; n_rec = 0; n_cmp = 0; overlap = false; invalid = false;
         prev_valid = false; prev_is = false; prev_pos = 0;
         next_row = NO_POS; carry_s = 0; carry_ie = 0;
         bw_t = NO_POS;
 #pragma unroll
         for (int d = 0; d < D; d++) { sw[d] = 0; ew[d] = 0; }
+    }
+    template <bool PATCH>
+    __device__ __forceinline__ void scan_end() {
+        if (!invalid) { close_gap<PATCH>(); if (!PATCH) flush_bitmap_words(); }
+    }
+    // fw0 / fw1: granule flags 0..63 of this string; further words come from the flag buffer `flags`
+    template <bool PATCH>
+    __device__ __forceinline__ void scan(uint32_t fw0, uint32_t fw1, const uint32_t* flags) {
+        scan_begin();
         for (uint32_t w = 0; w < p.fm_words && !invalid; w++) {
             const uint32_t fw = w == 0 ? fw0 : w == 1 ? fw1 : __ldcg(flags + (size_t)w * p.n_strings + j);
             uint32_t bits = fw;
@@ -372,7 +379,7 @@ struct LaneString {
                 scan_granule<PATCH>(w * 32 + g, (fw >> (g ^ 1u)) & 1u);
             }
         }
-        if (!invalid) { close_gap<PATCH>(); if (!PATCH) flush_bitmap_words(); }
+        scan_end<PATCH>();
     }
 
     // ---- masks ---------------------------------------------------------------------------------------------------------

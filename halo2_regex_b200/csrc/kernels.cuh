@@ -24,6 +24,7 @@ struct DefDev {
     uint32_t accepted_state;
     uint32_t sid_offset;
     uint32_t num_substrs;
+    const uint16_t* init_states;     // segment mode: state in which string j starts (null: first_state)
     uint32_t hot_states[2];          // bit s: some transition out of state s (< 64) carries a substr id (emit.cuh prefilter)
     unsigned long long* hist;        // dense [256][S] multiplicity bins (global, u64)
     unsigned long long* ep_start;    // [num_substrs][S] start-endpoint counters
@@ -70,6 +71,8 @@ struct WalkParams {
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
     uint32_t emit_smem_tables;       // 1: emit_kernel stages byte_class / trans in shared memory
+    uint32_t segment_mode;           // 1: the "strings" are consecutive chunks of ONE long string (long.cuh): string j starts in
+                                     //    init_states[j], stores only its own rows (the last one also the final state), no emit stage
     uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
     uint32_t prefilled;              // 1: the sparse columns were zeroed before emit_kernel (memset on a side stream, overlapping the walk)
     uint32_t debug;                  // timing experiments only (B2R_DEBUG env): emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status

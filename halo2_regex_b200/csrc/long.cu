@@ -1,0 +1,232 @@
+// Launchers of the long-string path (long.cuh).
+#include "long.cuh"
+
+#include <type_traits>
+#include <vector>
+
+#include "defs.hpp"
+#include "emit.cuh"
+
+namespace b2r {
+
+// chunk offsets for the walk kernel
+__global__ void long_offsets_kernel(uint64_t* offsets, uint32_t n_chunks, uint64_t len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_chunks) { const uint64_t o = (uint64_t)i * LONG_CHUNK; offsets[i] = o < len ? o : len; }
+}
+
+// f_k[s] for every chunk k and state s in [0, S]; S is the trap state (an invalid transition, sticky)
+__global__ void __launch_bounds__(256) long_maps_kernel(const __grid_constant__ LongParams p, uint32_t d) {
+    const uint32_t S = p.def[d].num_states, S1 = S + 1;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)p.n_chunks * S1) return;
+    const uint32_t k = (uint32_t)(t / S1);
+    uint32_t s = (uint32_t)(t % S1);
+    const uint64_t a = (uint64_t)k * LONG_CHUNK;
+    const uint64_t b = a + LONG_CHUNK < p.len ? a + LONG_CHUNK : p.len;
+    const uint8_t* cls = p.def[d].byte_class;
+    const uint32_t* tr = p.def[d].trans;
+    for (uint64_t i = a; i < b && s < S; i++) {
+        const uint32_t e = __ldg(tr + (uint32_t)__ldg(cls + __ldg(p.bytes + i)) * S + s);
+        s = (e & ENT_INVALID) ? S : (e & ENT_NEXT_MASK);
+    }
+    p.def[d].maps[t] = (uint16_t)s;
+}
+
+// level l+1 map i = composition of its (up to 64) children at level l; thread per (node, state)
+__global__ void __launch_bounds__(256) long_compose_kernel(const uint16_t* child_maps, uint16_t* parent_maps, uint32_t n_child, uint32_t n_parent, uint32_t S1) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_parent * S1) return;
+    const uint32_t i = t / S1;
+    uint32_t s = t % S1;
+    const uint32_t c0 = i * LONG_FANOUT, c1 = c0 + LONG_FANOUT < n_child ? c0 + LONG_FANOUT : n_child;
+    for (uint32_t c = c0; c < c1; c++) s = child_maps[(size_t)c * S1 + s];
+    parent_maps[t] = (uint16_t)s;
+}
+
+// entry states of the children of every node at level l+1, given the node's own entry state; thread per parent node
+__global__ void __launch_bounds__(256) long_propagate_kernel(const uint16_t* child_maps, const uint16_t* parent_entry, uint16_t* child_entry, uint32_t n_child,
+                                                              uint32_t n_parent, uint32_t S1) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parent) return;
+    uint32_t s = parent_entry[i];
+    const uint32_t c0 = i * LONG_FANOUT, c1 = c0 + LONG_FANOUT < n_child ? c0 + LONG_FANOUT : n_child;
+    for (uint32_t c = c0; c < c1; c++) { child_entry[c] = (uint16_t)s; s = child_maps[(size_t)c * S1 + s]; }
+}
+
+// bit c of word w: chunk 32w + c has a flagged granule
+__global__ void __launch_bounds__(256) long_summary_kernel(const uint32_t* fmask, uint32_t fm_words, uint32_t n_chunks, uint32_t* summary) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t any = 0;
+    if (c < n_chunks)
+        for (uint32_t w = 0; w < fm_words; w++) any |= fmask[(size_t)w * n_chunks + c];
+    const uint32_t word = __ballot_sync(0xffffffffu, any != 0);
+    if ((threadIdx.x & 31) == 0 && c < n_chunks) summary[c >> 5] = word;
+}
+
+// One warp: the emit stage of the single long string.  `p` describes the string as ONE string (n_strings = 1, offsets = {0, len},
+// max_chars = len + 1); fmask holds the granule flags per chunk: word w of chunk c at fmask[w * n_chunks + c].
+template <int D, typename ST>
+__global__ void __launch_bounds__(32) long_emit_kernel(const __grid_constant__ WalkParams p, const uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words) {
+    extern __shared__ __align__(16) unsigned char esmem[];
+    const int lane = threadIdx.x;
+    EmitTables<D> tb;
+    emit_tables_init<D>(p, esmem, tb);
+    __syncthreads();
+    const uint32_t L = p.max_chars - 1;
+    constexpr uint32_t GPC = LONG_CHUNK / 16;                            // granules per chunk
+    LaneString<D, ST> ls(p, tb, 0, p.bytes, L);
+    uint32_t r_nrec = 0, r_ncmp = 0, r_flags = 0;
+    bool patch = false;
+    auto pass = [&](auto patch_tag) {
+        constexpr bool PATCH = decltype(patch_tag)::value;
+        ls.scan_begin();
+        bool stop = false;                                               // warp-uniform: lane 0 hit an invalid transition
+        const uint32_t n_words = (n_chunks + 31) / 32;
+        for (uint32_t w0 = 0; w0 < n_words && !stop; w0 += 32) {         // 32 summary words at a time, one per lane
+            const uint32_t mine = w0 + lane < n_words ? summary[w0 + lane] : 0u;
+            uint32_t lanes = __ballot_sync(0xffffffffu, mine != 0);
+            while (lanes && !stop) {
+                const int l = __ffs((int)lanes) - 1;
+                lanes &= lanes - 1;
+                uint32_t chunks = __shfl_sync(0xffffffffu, mine, l);
+                while (chunks && !stop) {
+                    const uint32_t c = (w0 + l) * 32 + ((uint32_t)__ffs((int)chunks) - 1u);
+                    chunks &= chunks - 1;
+                    if (lane == 0) {
+                        for (uint32_t w = 0; w < chunk_fm_words && !ls.invalid; w++) {
+                            const uint32_t fw = p.fmask[(size_t)w * n_chunks + c];
+                            uint32_t bits = fw;
+                            while (bits && !ls.invalid) {
+                                const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
+                                bits &= bits - 1;
+                                ls.template scan_granule<PATCH>(c * GPC + w * 32 + g, (fw >> (g ^ 1u)) & 1u);
+                            }
+                        }
+                    }
+                    stop = __shfl_sync(0xffffffffu, (int)ls.invalid, 0) != 0;
+                }
+            }
+        }
+        if (lane == 0) ls.template scan_end<PATCH>();
+    };
+    pass(std::false_type{});
+    if (lane == 0) {
+        if (ls.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
+        else {
+            if (ls.overlap) r_flags = B2R_ST_OVERLAP;
+            patch = ls.n_seg > EMIT_NSEG;
+            if (!patch) { ls.write_masks(); r_nrec = ls.n_rec; r_ncmp = ls.n_cmp; }
+        }
+    }
+    if (__any_sync(0xffffffffu, patch)) {
+        pass(std::true_type{});
+        if (lane == 0) { r_nrec = ls.n_rec; r_ncmp = ls.n_cmp; }
+    }
+    if (lane == 0) {
+        uint32_t fin[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            fin[d] = (uint32_t)__ldcg(reinterpret_cast<const ST*>(p.def[d].states) + L);
+            if (fin[d] >= p.def[d].num_states) r_flags = B2R_ST_INVALID_TRANSITION;
+        }
+        if (r_flags & B2R_ST_INVALID_TRANSITION) kill_string(p, 0);
+        else {
+            uint32_t flags = r_flags;
+#pragma unroll
+            for (int d = 0; d < D; d++)
+                if (fin[d] == p.def[d].accepted_state) flags |= B2R_ST_ACCEPTED(d);
+            if (p.records && r_nrec > p.max_records) flags |= B2R_ST_RECORDS_TRUNCATED;
+            if (p.compact_bytes && r_ncmp > p.compact_pitch) flags |= B2R_ST_COMPACT_TRUNCATED;
+            if (p.status) {
+                b2r_string_status st = {};
+                st.flags = flags; st.err_pos = NO_POS; st.n_records = r_nrec; st.n_compact = r_ncmp;
+                p.status[0] = st;
+            }
+            atomicAdd(&p.counters->pad_rows, 1ull);                      // row len is the only row with enable = 0
+            atomicAdd(&p.counters->n_ok_strings, 1ull);
+            if (r_flags & B2R_ST_OVERLAP) atomicAdd(&p.counters->n_overlap, 1ull);
+        }
+    }
+    EmitTotals none;
+    emit_publish<D>(p, tb, none);
+}
+
+
+size_t long_level_nodes(uint32_t n_chunks) {
+    size_t total = 0;
+    for (uint32_t n = n_chunks;; n = (n + LONG_FANOUT - 1) / LONG_FANOUT) { total += n; if (n <= 1) break; }
+    return total;
+}
+
+#define LAUNCH_CHECK(what)                                                                                     \
+    do {                                                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                                   \
+        if (e_ != cudaSuccess) { set_error(what " launch: %s", cudaGetErrorString(e_)); return B2R_ERR_CUDA; } \
+    } while (0)
+
+// chunk offsets, chunk maps, the composition tree and the entry states of every chunk (level 0 of `entry`)
+int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long_offsets_kernel<<<(lp.n_chunks + 1 + 255) / 256, 256, 0, st>>>(lp.offsets, lp.n_chunks, lp.len);
+    LAUNCH_CHECK("long_offsets_kernel"); (*launches)++;
+    for (uint32_t d = 0; d < lp.n_defs; d++) {
+        const uint32_t S1 = lp.def[d].num_states + 1;
+        const uint64_t threads = (uint64_t)lp.n_chunks * S1;
+        long_maps_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d);
+        LAUNCH_CHECK("long_maps_kernel"); (*launches)++;
+        // up the tree
+        std::vector<uint32_t> n_level{lp.n_chunks};
+        std::vector<size_t> off_level{0};
+        while (n_level.back() > 1) {
+            off_level.push_back(off_level.back() + n_level.back());
+            n_level.push_back((n_level.back() + LONG_FANOUT - 1) / LONG_FANOUT);
+        }
+        for (size_t l = 0; l + 1 < n_level.size(); l++) {
+            const uint32_t nc = n_level[l], np = n_level[l + 1];
+            long_compose_kernel<<<(np * S1 + 255) / 256, 256, 0, st>>>(lp.def[d].maps + off_level[l] * S1, lp.def[d].maps + off_level[l + 1] * S1, nc, np, S1);
+            LAUNCH_CHECK("long_compose_kernel"); (*launches)++;
+        }
+        // the root starts in first_state; down the tree
+        const uint16_t first = (uint16_t)lp.def[d].first_state;
+        if (cudaMemcpyAsync(lp.def[d].entry + off_level.back(), &first, 2, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("cudaMemcpyAsync(entry)"); return B2R_ERR_CUDA; }
+        for (size_t l = n_level.size() - 1; l-- > 0;) {
+            const uint32_t nc = n_level[l], np = n_level[l + 1];
+            long_propagate_kernel<<<(np + 255) / 256, 256, 0, st>>>(lp.def[d].maps + off_level[l] * S1, lp.def[d].entry + off_level[l + 1], lp.def[d].entry + off_level[l], nc, np, S1);
+            LAUNCH_CHECK("long_propagate_kernel"); (*launches)++;
+        }
+    }
+    return B2R_OK;
+}
+
+template <int D, typename ST>
+static int launch_long_emit_one(const WalkParams& p, const uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, cudaStream_t st) {
+    const size_t smem = emit_smem_bytes(p);
+    auto kern = long_emit_kernel<D, ST>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(long_emit_kernel): %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
+    }
+    kern<<<1, 32, smem, st>>>(p, summary, n_chunks, chunk_fm_words);
+    LAUNCH_CHECK("long_emit_kernel");
+    return B2R_OK;
+}
+
+int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary);
+    LAUNCH_CHECK("long_summary_kernel"); (*launches)++;
+    (*launches)++;
+#define GO(D_) return wide ? launch_long_emit_one<D_, uint16_t>(p, summary, n_chunks, chunk_fm_words, st) : launch_long_emit_one<D_, uint8_t>(p, summary, n_chunks, chunk_fm_words, st)
+    switch (p.n_defs) {
+        case 1: GO(1);
+        case 2: GO(2);
+        case 3: GO(3);
+        case 4: GO(4);
+    }
+#undef GO
+    set_error("unsupported number of defs %u", p.n_defs);
+    return B2R_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2r

@@ -1,0 +1,46 @@
+// Long-string path (b2r_match_long; BASELINE config "single 64 MiB string"): ONE string of `len` bytes, M = len + 1 rows.
+//
+// The walk is a dependent chain over the whole string, so it is cut into chunks of LONG_CHUNK bytes:
+//   1. long_maps_kernel      every chunk's transition vector f_k : S -> S (state after the chunk for EVERY state before
+//                            it), one thread per (chunk, state);
+//   2. long_compose_kernel   parallel-prefix composition, 64-ary tree: level l+1 map i = f of its 64 children composed;
+//      long_propagate_kernel back down the tree: the state in which every node starts, from first_state at the root;
+//   3. walk_kernel           in segment mode: chunk k is "string" k, starts in its now-known entry state, writes its slice
+//                            of the single state row, its granule flags and the multiplicity bins (walk.cuh);
+//   4. long_summary_kernel + long_emit_kernel   the emit stage for one string whose flags are spread over the chunks:
+//                            one warp, flagged granules visited in order (emit.cuh's LaneString), after the sparse
+//                            columns were zeroed with a memset.  The boundary stream of the mask algebra is sequential;
+//                            the flagged granules are few.
+#pragma once   // declarations only: the kernels live in long.cu
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace b2r {
+
+constexpr uint32_t LONG_CHUNK = 1024;      // bytes per chunk: a multiple of 32 (whole 32-row windows), <= 1024 (two flag words)
+constexpr uint32_t LONG_FANOUT = 64;
+
+struct LongParams {
+    const uint8_t* bytes;
+    uint64_t len;
+    uint32_t n_chunks;
+    uint32_t n_defs;
+    struct {
+        const uint8_t* byte_class;
+        const uint32_t* trans;           // [C][S] packed entries (defs.hpp)
+        uint32_t num_states, first_state;
+        uint16_t* maps;                  // all levels back to back: level 0 [n_chunks][S+1], level 1 [ceil(n/64)][S+1], ...
+        uint16_t* entry;                 // all levels back to back: entry state of every node
+    } def[B2R_MAX_DEFS];
+    uint64_t* offsets;                   // [n_chunks + 1]
+};
+
+// host-callable (long.cu)
+int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches);
+int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches);
+size_t long_level_nodes(uint32_t n_chunks);   // total nodes over all tree levels
+
+}  // namespace b2r

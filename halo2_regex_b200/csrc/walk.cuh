@@ -240,7 +240,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 
         uint32_t cur[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) cur[d] = (p.def[d].first_state << 16) | (p.def[d].first_state * stride);
+        for (int d = 0; d < D; d++) {
+            const uint32_t f = (p.def[d].init_states && valid) ? (uint32_t)p.def[d].init_states[idx] : p.def[d].first_state;
+            cur[d] = (f << 16) | (f * stride);
+        }
 
         // staging geometry
         const uint32_t shift = (uint32_t)(off & 15);
@@ -425,7 +428,12 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 for (int i = 0; i < VPS; i++) {
                     const int row = sr0 + (32 / VPS) * i;
                     const uint32_t elem = cbase + (uint32_t)skv * (16 / SB);   // first row-element of this vector
-                    if (row < (int)rows_here && elem < Mpad) {
+                    bool mine = row < (int)rows_here && elem < Mpad;
+                    if (p.segment_mode) {   // a chunk of a long string owns rows [0, len) only; the last chunk also the final-state row
+                        const uint32_t rl = __shfl_sync(0xffffffffu, L, row);
+                        mine = mine && (elem < rl || (tile_base + row + 1 == p.n_strings && elem < ((rl + 16u) & ~15u)));
+                    }
+                    if (mine) {
                         const uint4 v = lds128(INPLACE ? in_s + (chunk & 1) * (32 * PITCH) + row * PITCH + skv * 16 : st_s + (d * 32 + row) * SPITCH + skv * 16);
                         *reinterpret_cast<uint4*>(col + ((tile_base + row) * rp + elem) * SB) = v;
                     }

@@ -55,9 +55,9 @@ class AssignedRegexResult:
 class DeviceOutputs:
     """Caller-owned DEVICE buffers (torch tensors) for one batch, laid out as include/b2r.h `b2r_outputs` describes."""
 
-    def __init__(self, cfg, n_strings, row_pitch=None, bitmap_pitch=None, max_records=8, compact_pitch=64, want=None, device=None):
+    def __init__(self, cfg, n_strings, row_pitch=None, bitmap_pitch=None, max_records=8, compact_pitch=64, want=None, device=None, max_chars_size=None):
         import torch
-        self.cfg, self.n, self.m = cfg, int(n_strings), cfg.max_chars_size
+        self.cfg, self.n, self.m = cfg, int(n_strings), int(max_chars_size) if max_chars_size else cfg.max_chars_size   # max_chars_size: match_long (len + 1)
         self.row_pitch = int(row_pitch) if row_pitch else round_up(self.m, 32)
         self.bitmap_pitch = int(bitmap_pitch) if bitmap_pitch else round_up((self.m + 7) // 8, 32)
         want = set(want) if want else {"states", "substr_ids", "start_enable", "end_enable", "masked_chars", "masked_substr_ids",
@@ -239,6 +239,17 @@ class RegexVerifyConfig:
         n = d_offsets.numel() - 1
         st = out.struct(flags)
         rc = lib.b2r_match_batch(self._h, d_bytes.data_ptr(), d_offsets.data_ptr(), n, d_bytes.numel(), C.byref(st), stream.cuda_stream)
+        _raise(rc)
+        return out
+
+    def match_long_device(self, d_bytes, out, stream=None):
+        """b2r_match_long: ONE string (the whole of `d_bytes`, a device tensor) with max_chars_size = len + 1; `out` is a
+        DeviceOutputs(cfg, 1, max_chars_size=len + 1).  Asynchronous on `stream`."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_bytes.device)
+        st = out.struct(0)
+        rc = lib.b2r_match_long(self._h, d_bytes.data_ptr(), d_bytes.numel(), C.byref(st), stream.cuda_stream)
         _raise(rc)
         return out
 

@@ -300,3 +300,48 @@ def test_multiplicity_invariant_full_size_property():
     j = int(np.nonzero(plan["has_match"])[0][5])
     o, nl = int(plan["offset"][j]) + 21, int(plan["name_len"][j])
     assert bytes(mc[j, o:o + nl]) == bytes(h_data[j, o:o + nl])
+
+
+@pytest.mark.parametrize("set_name,length", [("regex2", 0), ("regex2", 1), ("regex2", 1023), ("regex2", 1024), ("regex2", 1025), ("regex2", 70000),
+                                             ("regex1", 5000), ("test1", 40000), ("regex3_k3", 3333)])
+def test_long_string_path(set_name, length):
+    """b2r_match_long (BASELINE config 3 at reduced size): one string cut into 1 KiB chunks, transition vectors composed by
+    parallel prefix, chunk walks from the resolved entry states, ordered emit - against the oracle on the same single string
+    with max_chars_size = len + 1."""
+    import torch
+    import halo2_regex_b200 as H
+    rng = random.Random(length * 7 + len(set_name))
+    alphabet = bytes([9, 10, 13] + list(range(32, 127)))
+    body = bytearray(rng.choice(alphabet) for _ in range(length))
+    for snip in SNIPPETS:                                   # plant matches, some of them across chunk boundaries
+        for _ in range(3):
+            if length > len(snip) + 2:
+                at = rng.choice([rng.randrange(0, length - len(snip)), max(0, min(length - len(snip), 1024 * rng.randrange(0, length // 1024 + 1) - rng.randrange(0, len(snip))))])
+                body[at:at + len(snip)] = snip
+    s = bytes(body)
+    M = length + 1
+    cfg, ocfg = product_config(set_name, 64), oracle_config(set_name, M)      # the handle's own max_chars_size is ignored
+    d = torch.from_numpy(np.frombuffer(s + b"\0" * 16, dtype=np.uint8).copy()).cuda()[:length]
+    out = H.DeviceOutputs(cfg, 1, max_records=64, compact_pitch=256, max_chars_size=M)
+    cfg.match_long_device(d, out)
+    res = cfg.batch_result(check=False)
+    data, offs = _pack([s])
+    o, ores = ocfg.match_batch(data, offs, max_records=64, compact_pitch=256)
+    assert res.code == ores.code
+    assert H.compare_outputs(out.to_host(), o) == []
+
+
+def test_long_string_invalid_transition():
+    import torch
+    import halo2_regex_b200 as H
+    s = b"email was meant for @vitalik." * 3 + b"\x01" + b"abc" * 2000
+    M = len(s) + 1
+    cfg, ocfg = product_config("regex1", 64), oracle_config("regex1", M)
+    d = torch.from_numpy(np.frombuffer(s, dtype=np.uint8).copy()).cuda()
+    out = H.DeviceOutputs(cfg, 1, max_chars_size=M)
+    cfg.match_long_device(d, out)
+    res = cfg.batch_result(check=False)
+    data, offs = _pack([s])
+    o, ores = ocfg.match_batch(data, offs)
+    assert res.code == ores.code == H._abi.B2R_ERR_INVALID_TRANSITION
+    assert (res.pos, res.state, res.byte) == (ores.pos, ores.state, ores.byte)
