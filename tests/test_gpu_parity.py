@@ -345,3 +345,40 @@ def test_long_string_invalid_transition():
     o, ores = ocfg.match_batch(data, offs)
     assert res.code == ores.code == H._abi.B2R_ERR_INVALID_TRANSITION
     assert (res.pos, res.state, res.byte) == (ores.pos, ores.state, ores.byte)
+
+
+@pytest.mark.parametrize("set_name", ["regex3", "regex3_k3", "three"])
+def test_config2_shape(set_name):
+    """BASELINE config 2 at reduced N: from: header lines through regex3 — reading (i) regex3 + substr1..3 in one RegexDefs,
+    reading (ii) three RegexDefs."""
+    from halo2_regex_b200 import workloads as W
+    data, plan = W.config2_numpy(768, 1024)
+    strings = [bytes(r) for r in data]
+    cfg, g, o = _both(set_name, 1025, strings, compact_pitch=32)
+    d = len(DEF_SETS[set_name]) - 1
+    assert ((g.status["flags"] >> d) & 1).all()                      # every string ends in a well-formed from: line
+    j = 5
+    a0 = int(plan["addr_start"][j])
+    addr = bytes(plan["addr"][j]).rstrip(b"\0")
+    assert bytes(g.masked_chars[j, a0:a0 + len(addr)]) == addr
+
+
+def test_config4_large_dfa():
+    """BASELINE config 4 at reduced N: a synthetic DFA with 1023 states in the reference's text format (2-byte state column,
+    tables beyond the replicated shared-memory layout), 4 KiB strings."""
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    from halo2_regex_b200 import workloads as W
+    allstr, substr, info = W.large_dfa_texts()
+    assert info["states"] >= 512
+    M = 4097
+    cfg = H.RegexVerifyConfig.configure(M, [H.RegexDefs(H.AllstrRegexDef.read_from_reader(allstr), [H.SubstrRegexDef.read_from_reader(substr)])])
+    assert cfg.state_widths == [2]
+    ocfg = O.OracleConfig([(O.OracleAllstr(allstr), [O.OracleSubstr(substr)])], M)
+    data, plan = W.config4_numpy(96, 4096)
+    flat, offs = data.reshape(-1), np.arange(97, dtype=np.uint64) * 4096
+    g, gres = cfg.match_batch_host(flat, offs, max_records=4, compact_pitch=64, fill=0xCD)
+    o, ores = ocfg.match_batch(flat, offs, max_records=4, compact_pitch=64)
+    assert gres.code == ores.code == 0
+    assert H.compare_outputs(g, o) == []
+    assert np.array_equal((g.status["flags"] & 1).astype(bool), plan["has_from"])
