@@ -145,11 +145,15 @@ def main():
     ap.add_argument("--log2-strings", type=int, default=LOG2_STRINGS, help="strings per GPU (default: the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of one CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -165,6 +169,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -181,15 +187,39 @@ def main():
     algo_bytes = in_bytes + n * 8 + out.written_bytes()     # input + offsets read, every witness column written (M rows/string)
     stream = torch.cuda.current_stream(dev)
 
-    def step():
-        cfg.match_batch_device(d_bytes, d_offs, out, stream=stream)
+    def enqueue():
+        cfg.match_batch_device(d_bytes, d_offs, out, stream=torch.cuda.current_stream(dev))
         if world > 1:
             allreduce_multiplicities(out.mult + out.endpoint_mult)            # the path's only exchange (NCCL over NVLink)
 
     for _ in range(args.warmup):
-        step()
+        enqueue()
     assert cfg.batch_result(stream=stream).code == 0
     launches_per_step = cfg.last_launch_count()
+    # One step = a handful of launches (2 memset nodes, walk_kernel, finalize_kernel): on one GPU they are captured in a CUDA
+    # graph so that the step is one launch.  (With the NCCL all-reduce inside, the captured step was slower and the process
+    # group hung at teardown, so N > 1 times plain launches.)
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e!r}); timing plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            enqueue()
+
+    for _ in range(2):
+        step()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
@@ -218,6 +248,12 @@ def main():
     step_ms = sorted(a_.elapsed_time(b_) for a_, b_ in ev)
     assert cfg.batch_result(stream=stream).code == 0
 
+    # size-independent check at full size (the oracle is the checker only in tests/ at small sizes): the all-reduced
+    # multiplicities of the last timed step cover every row of every rank
+    mult = out.mult[0].cpu().numpy().astype(np.uint64)
+    all_rows = n * M * (world if world > 1 else 1)
+    assert int(mult.sum()) == all_rows, (int(mult.sum()), all_rows)
+
     # the dominant kernel alone (walk_kernel with the emit stage fused in), CUDA events on the launching stream inside the library
     cfg.set_timing(True)
     walk, stages = [], []
@@ -229,11 +265,6 @@ def main():
     cfg.set_timing(False)
     walk_ms = sum(walk) / len(walk)
     plan = cfg.last_plan()
-
-    # size-independent checks at full size (the oracle is the checker only in tests/ at small sizes)
-    mult = out.mult[0].cpu().numpy().astype(np.uint64)
-    per_rank_rows = n * M * (world if world > 1 else 1)
-    assert int(mult.sum()) == per_rank_rows, (int(mult.sum()), per_rank_rows)
 
     # ---- end-to-end arm: C-ABI call with pinned host buffers -----------------------------------------------------------
     e2e = None
@@ -300,7 +331,8 @@ def main():
         "config": {"workload": "regex1_test + substr1, 2^%d x 1 KiB strings per GPU, M=1025 (BASELINE configs[1])" % args.log2_strings,
                    "strings_per_gpu": n, "string_len": L, "max_chars_size": M, "defs": 1, "states": 29,
                    "l2_policy": "inputs (1 GiB) + outputs (4.6 GB) per step exceed the 126 MB L2; no flush needed",
-                   "parallelism": f"strings sharded over {world} GPU(s); NCCL all-reduce of multiplicities only" if world > 1 else "1 GPU"},
+                   "parallelism": f"strings sharded over {world} GPU(s); NCCL all-reduce of multiplicities only" if world > 1 else "1 GPU",
+                   "cuda_graph": graph is not None},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps * world,
@@ -313,7 +345,7 @@ def main():
                      "bytes_per_input_byte": algo_bytes / in_bytes, "peak_source": peak_src},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
