@@ -79,6 +79,10 @@ struct b2r_config {
     DevBuf ws_bytes, ws_offsets, ws_cols;
     cudaStream_t host_stream = nullptr;
     cudaStream_t fill_stream = nullptr;   // zero-fill of the sparse columns, overlapping the walk
+    cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host entry point: H2D / D2H copies overlapping the kernels
+    static constexpr int MAX_SLICES = 8;
+    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
+    BatchCounters* h_slices = nullptr;    // pinned: the counters of every slice of a host batch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
@@ -340,6 +344,11 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         if (rc) return rc;
         CUDA_TRY(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->fill_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaMallocHost((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -358,6 +367,11 @@ void b2r_config_free(b2r_config* c) {
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         if (c->fill_stream) cudaStreamDestroy(c->fill_stream);
+        if (c->in_stream) cudaStreamDestroy(c->in_stream);
+        if (c->out_stream) cudaStreamDestroy(c->out_stream);
+        for (auto& e : c->ev_in) if (e) cudaEventDestroy(e);
+        for (auto& e : c->ev_done) if (e) cudaEventDestroy(e);
+        if (c->h_slices) cudaFreeHost(c->h_slices);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         if (c->ev_join) cudaEventDestroy(c->ev_join);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -501,7 +515,7 @@ int b2r_match_batch_host(b2r_config* c, const uint8_t* h_bytes, const uint64_t* 
     const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
     size_t need = 0;
     auto slot = [&](size_t bytes) { size_t o = need; need += align_up(bytes, 256); return o; };
-    struct Copy { size_t off; void* host; size_t bytes; };
+    struct Copy { size_t off; void* host; size_t bytes; size_t stride; };   // stride: bytes per string (0: not per string)
     std::vector<Copy> copies;
     b2r_outputs dout = *ho;
     size_t off_states[B2R_MAX_DEFS], off_sid[B2R_MAX_DEFS], off_se[B2R_MAX_DEFS], off_ee[B2R_MAX_DEFS], off_mult[B2R_MAX_DEFS], off_em[B2R_MAX_DEFS];
@@ -520,18 +534,18 @@ int b2r_match_batch_host(b2r_config* c, const uint8_t* h_bytes, const uint64_t* 
     const size_t off_cb = ho->compact_bytes ? slot(n * (size_t)ho->compact_pitch) : 0;
     if ((rc = c->ws_cols.reserve(need + 256))) return rc;
     unsigned char* cb = (unsigned char*)c->ws_cols.p;
-    auto bind = [&](void* host, size_t off, size_t bytes) -> void* {
+    auto bind = [&](void* host, size_t off, size_t bytes, size_t stride = 0) -> void* {
         if (!host) return nullptr;
-        copies.push_back({off, host, bytes});
+        copies.push_back({off, host, bytes, stride});
         return cb + off;
     };
     const bool acc = (ho->flags & B2R_OUT_ACCUMULATE_MULT) != 0;
     for (uint32_t d = 0; d < c->n_defs; d++) {
         const size_t w = c->packed[d].state_width;
-        dout.states[d] = bind(ho->states[d], off_states[d], n * rp * w);
-        dout.substr_ids[d] = (uint8_t*)bind(ho->substr_ids[d], off_sid[d], n * rp);
-        dout.start_enable[d] = (uint8_t*)bind(ho->start_enable[d], off_se[d], n * bp);
-        dout.end_enable[d] = (uint8_t*)bind(ho->end_enable[d], off_ee[d], n * bp);
+        dout.states[d] = bind(ho->states[d], off_states[d], n * rp * w, rp * w);
+        dout.substr_ids[d] = (uint8_t*)bind(ho->substr_ids[d], off_sid[d], n * rp, rp);
+        dout.start_enable[d] = (uint8_t*)bind(ho->start_enable[d], off_se[d], n * bp, bp);
+        dout.end_enable[d] = (uint8_t*)bind(ho->end_enable[d], off_ee[d], n * bp, bp);
         dout.mult[d] = (uint64_t*)bind(ho->mult[d], off_mult[d], c->packed[d].rows.size() * 8);
         dout.endpoint_mult[d] = (uint64_t*)bind(ho->endpoint_mult[d], off_em[d], c->packed[d].erows.size() * 16);
         if (acc) {
@@ -539,25 +553,84 @@ int b2r_match_batch_host(b2r_config* c, const uint8_t* h_bytes, const uint64_t* 
             if (ho->endpoint_mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.endpoint_mult[d], ho->endpoint_mult[d], c->packed[d].erows.size() * 16, cudaMemcpyHostToDevice, st));
         }
     }
-    dout.masked_chars = (uint8_t*)bind(ho->masked_chars, off_mc, n * rp);
-    dout.masked_substr_ids = (uint8_t*)bind(ho->masked_substr_ids, off_ms, n * rp);
-    dout.status = (b2r_string_status*)bind(ho->status, off_st, n * sizeof(b2r_string_status));
-    dout.records = (b2r_substr_record*)bind(ho->records, off_rec, n * (size_t)ho->max_records * sizeof(b2r_substr_record));
-    dout.compact_bytes = (uint8_t*)bind(ho->compact_bytes, off_cb, n * (size_t)ho->compact_pitch);
+    dout.masked_chars = (uint8_t*)bind(ho->masked_chars, off_mc, n * rp, rp);
+    dout.masked_substr_ids = (uint8_t*)bind(ho->masked_substr_ids, off_ms, n * rp, rp);
+    dout.status = (b2r_string_status*)bind(ho->status, off_st, n * sizeof(b2r_string_status), sizeof(b2r_string_status));
+    dout.records = (b2r_substr_record*)bind(ho->records, off_rec, n * (size_t)ho->max_records * sizeof(b2r_substr_record), (size_t)ho->max_records * sizeof(b2r_substr_record));
+    dout.compact_bytes = (uint8_t*)bind(ho->compact_bytes, off_cb, n * (size_t)ho->compact_pitch, (size_t)ho->compact_pitch);
 
-    // inputs: keep the caller's offsets (the kernel adds them to the base pointer, so shift the base instead)
-    if (nbytes) CUDA_TRY(cudaMemcpyAsync((unsigned char*)c->ws_bytes.p + (base & 15), h_bytes + base, nbytes, cudaMemcpyHostToDevice, st));
-    if (n) CUDA_TRY(cudaMemcpyAsync(c->ws_offsets.p, h_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    // The batch is cut into slices of strings: the H2D copy of slice i+1 and the D2H copy of slice i-1 run on their own
+    // streams while the kernels of slice i run (PCIe is full duplex; the copies are the end-to-end bottleneck).
+    // inputs: keep the caller's offsets (the kernel adds them to the base pointer, so shift the base instead):
     // d_bytes + offsets[j] must address string j: d_bytes = ws + (base & 15) - base  (16-byte aligned by construction)
-    const uint8_t* d_bytes = (const uint8_t*)c->ws_bytes.p + (base & 15) - base;
-    rc = match_batch_impl(c, d_bytes, (const uint64_t*)c->ws_offsets.p, n, total, &dout, c->max_chars, st);
-    if (rc) return rc;
+    unsigned char* const d_in = (unsigned char*)c->ws_bytes.p + (base & 15);
+    const uint8_t* d_bytes = d_in - base;
+    const uint64_t* d_offsets = (const uint64_t*)c->ws_offsets.p;
+    const int n_slices = n >= 16384 ? b2r_config::MAX_SLICES : 1;
+    CUDA_TRY(cudaEventRecord(c->ev_fork, st));                           // accumulate uploads / earlier work on the compute stream
+    CUDA_TRY(cudaStreamWaitEvent(c->in_stream, c->ev_fork, 0));
+    CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_fork, 0));
+    if (n) CUDA_TRY(cudaMemcpyAsync(c->ws_offsets.p, h_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->in_stream));
+    std::vector<WalkParams> slice_params(n_slices);
+    std::vector<uint64_t> slice_lo(n_slices);
+    for (int i = 0; i < n_slices; i++) {
+        const uint64_t lo = n * (uint64_t)i / n_slices, hi = n * (uint64_t)(i + 1) / n_slices, ni = hi - lo;
+        slice_lo[i] = lo;
+        const uint64_t b0 = n ? h_offsets[lo] : 0, b1 = n ? h_offsets[hi] : 0;
+        if (b1 < b0) { set_error("offsets must be non-decreasing"); return B2R_ERR_INVALID_ARG; }
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_in + (b0 - base), h_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, c->in_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_in[i], c->in_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[i], 0));
+        b2r_outputs ds = dout;                                           // this slice's rows of every column
+        for (uint32_t d = 0; d < c->n_defs; d++) {
+            const size_t w = c->packed[d].state_width;
+            if (ds.states[d]) ds.states[d] = (unsigned char*)ds.states[d] + lo * rp * w;
+            if (ds.substr_ids[d]) ds.substr_ids[d] += lo * rp;
+            if (ds.start_enable[d]) ds.start_enable[d] += lo * bp;
+            if (ds.end_enable[d]) ds.end_enable[d] += lo * bp;
+        }
+        if (ds.masked_chars) ds.masked_chars += lo * rp;
+        if (ds.masked_substr_ids) ds.masked_substr_ids += lo * rp;
+        if (ds.status) ds.status += lo;
+        if (ds.records) ds.records += lo * (size_t)ho->max_records;
+        if (ds.compact_bytes) ds.compact_bytes += lo * (size_t)ho->compact_pitch;
+        if (i > 0) ds.flags |= B2R_OUT_ACCUMULATE_MULT;                  // the multiplicities of the slices add up
+        rc = match_batch_impl(c, d_bytes, d_offsets + lo, ni, total, &ds, c->max_chars, st);
+        if (rc) return rc;
+        slice_params[i] = c->last;
+        CUDA_TRY(cudaMemcpyAsync(c->h_slices + i, c->scratch, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(c->ev_done[i], st));
+        CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_done[i], 0));
+        for (const Copy& cp : copies)
+            if (cp.stride && ni) CUDA_TRY(cudaMemcpyAsync((unsigned char*)cp.host + lo * cp.stride, cb + cp.off + lo * cp.stride, ni * cp.stride, cudaMemcpyDeviceToHost, c->out_stream));
+    }
     for (const Copy& cp : copies)
-        if (cp.bytes) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
+        if (!cp.stride && cp.bytes) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(c->out_stream));
+
+    // the batch result: the lowest failing string over all slices (reference: the first panic), overlaps summed
     b2r_batch_status r;
-    rc = b2r_batch_result(c, st, &r);
+    memset(&r, 0, sizeof r);
+    uint64_t n_overlap = 0;
+    for (int i = 0; i < n_slices; i++) n_overlap += c->h_slices[i].n_overlap;
+    for (int i = 0; i < n_slices; i++) {
+        if (c->h_slices[i].first_bad == ~0ull) continue;
+        rc = launch_diagnose(slice_params[i], c->h_slices[i].first_bad, c->d_batch_status, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(&r, c->d_batch_status, sizeof r, cudaMemcpyDeviceToHost));
+        r.string_idx += slice_lo[i];
+        if (r.code == B2R_ERR_INVALID_TRANSITION)
+            set_error("The transition from %u by %u is invalid! (string %llu, position %u, def %u)", r.state, (unsigned)r.byte,
+                      (unsigned long long)r.string_idx, r.pos, (unsigned)r.def);
+        else if (r.code == B2R_ERR_TOO_LONG)
+            set_error("string %llu is longer than max_chars_size-1", (unsigned long long)r.string_idx);
+        break;
+    }
+    r.n_overlap_lo = (uint32_t)n_overlap;
     if (result) *result = r;
-    return rc;
+    return r.code;
 }
 
 int b2r_match_substrs(b2r_config* c, const uint8_t* characters, uint64_t len, const b2r_outputs* h_out, b2r_batch_status* result) {

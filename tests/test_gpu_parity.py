@@ -382,3 +382,17 @@ def test_config4_large_dfa():
     assert gres.code == ores.code == 0
     assert H.compare_outputs(g, o) == []
     assert np.array_equal((g.status["flags"] & 1).astype(bool), plan["has_from"])
+
+
+def test_host_entry_point_slices():
+    """b2r_match_batch_host cuts large batches into slices (H2D / kernels / D2H overlap on three streams): same bits, the
+    multiplicities of the slices add up, and the batch result is the lowest failing string over all slices."""
+    rng = random.Random(99)
+    strings = _random_strings(rng, 20000, 60, SNIPPETS)
+    _both("test1", 61, strings)
+    bad = list(strings)
+    bad[17000] = b"email \x01"
+    bad[9000] = b"\x02"
+    cfg, g, o = _both("test1", 61, bad)
+    import halo2_regex_b200 as H
+    assert g.status["flags"][9000] & H._abi.B2R_ST_INVALID_TRANSITION and g.status["flags"][17000] & H._abi.B2R_ST_INVALID_TRANSITION
