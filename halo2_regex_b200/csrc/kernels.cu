@@ -63,7 +63,7 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     int rc = device_limits(&n_sm, &max_smem);
     if (rc) return rc;
     const uint32_t sb = wide ? 2 : 1;
-    auto fits = [&](uint32_t tm, uint32_t hm, int warps) {
+    auto fits_k = [&](uint32_t tm, uint32_t hm, int warps) {
         p.table_mode = tm; p.hist_mode = hm;
         if (tm != TABLE_GLOBAL) {
             const uint32_t stride = walk_stride(tm);
@@ -78,6 +78,13 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
             for (uint32_t d = 0; d < p.n_defs; d++) tabs += (uint64_t)p.def[d].num_classes * p.def[d].padded_states * walk_stride(tm);
         if (tabs > (uint64_t)max_smem) return false;
         return walk_smem_bytes(p, sb, warps) <= (size_t)max_smem;
+    };
+    // HIST_GLOBAL: the largest bin cache (4096 .. 256 slots per def) that leaves room for the warps
+    auto fits = [&](uint32_t tm, uint32_t hm, int warps) {
+        for (p.hist_cache_log2 = 12; p.hist_cache_log2 >= 8; p.hist_cache_log2--)
+            if (fits_k(tm, hm, warps)) return true;
+        p.hist_cache_log2 = 8;
+        return false;
     };
     static const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {TABLE_PLAIN, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL},
                                        {TABLE_PLAIN, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};

@@ -69,6 +69,7 @@ struct WalkParams {
     uint32_t fm_words;
     uint32_t table_mode;             // TABLE_REPL / TABLE_PLAIN / TABLE_GLOBAL (walk.cuh)
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
+    uint32_t hist_cache_log2;        // HIST_GLOBAL: log2 of the slots of the per-def shared-memory bin cache in front of L2
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
     uint32_t emit_smem_tables;       // 1: emit_kernel stages byte_class / trans in shared memory
     uint32_t segment_mode;           // 1: the "strings" are consecutive chunks of ONE long string (long.cuh): string j starts in
@@ -81,6 +82,8 @@ struct WalkParams {
 constexpr uint32_t TABLE_REPL = 0;   // shared memory, one copy of every entry per bank (stride 128 B): conflict-free lookups
 constexpr uint32_t TABLE_PLAIN = 1;  // shared memory, one copy (stride 4 B)
 constexpr uint32_t TABLE_GLOBAL = 2; // global memory (L1/L2)
+// HIST_SMEM: dense bins [state][byte] in shared memory.  HIST_GLOBAL (bins too large for that): 64-bit atomics on the global
+// bins, behind a shared-memory cache of (key, count) slots that absorbs the hot (byte, state) pairs.
 constexpr uint32_t HIST_NONE = 0, HIST_SMEM = 1, HIST_GLOBAL = 2;
 
 struct FinalizeParams {

@@ -80,7 +80,7 @@ __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { retu
 struct WalkLayout {
     uint32_t tab[B2R_MAX_DEFS];    // byte offsets from the aligned base; table rows are P*stride bytes and aligned to that
     uint32_t cls;                  // 256 entries of `stride` bytes
-    uint32_t hist[B2R_MAX_DEFS];   // (S+1) x 256 u32 bins per def
+    uint32_t hist[B2R_MAX_DEFS];   // (S+1) x 256 u32 bins per def (HIST_SMEM) / the bin cache (HIST_GLOBAL)
     uint32_t emit;                 // emit tables + endpoint counters (emit.cuh), fused mode
     uint32_t zero;                 // WALK_ZERO_BYTES of zeros, fused mode
     uint32_t tiles;                // first per-warp tile
@@ -105,6 +105,8 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
     }
     if (p.hist_mode == HIST_SMEM)
         for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
+    if (p.hist_mode == HIST_GLOBAL)   // bin cache: 2^log2 slots of {key, count}
+        for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += 8u << p.hist_cache_log2; }
     cur = walk_align_up(cur, 16);
     L.emit = cur;
     if (p.fuse) cur += emit_smem_bytes(p);
@@ -174,6 +176,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < D; d++)
             for (uint32_t i = threadIdx.x; i < (p.def[d].num_states + 1) * 256u; i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; d++)
+            for (uint32_t i = threadIdx.x; i < (2u << p.hist_cache_log2); i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
     }
     EmitTables<D> etb;
     const uint32_t zero_s = base_s + lay.zero;
@@ -215,11 +221,24 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> 16));
         }
     };
+    const uint32_t cache_log2 = p.hist_cache_log2;
     auto count = [&](int d, uint32_t cur, uint32_t c) {
         if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> 16) << 8) | c) * 4);
         else {
+            // bin cache: slot = {key, count}; a slot is claimed by the first key that hashes to it and never changes owner,
+            // every other key of that slot goes to the global bins (exact either way)
             const uint32_t s = cur >> 16;
-            if (s < p.def[d].num_states) atomicAdd(p.def[d].hist + (size_t)c * p.def[d].num_states + s, 1ull);
+            if (s < p.def[d].num_states) {
+                const uint32_t key = ((s << 8) | c) + 1u;
+                const uint32_t slot = hist_s[d] + (((key * 0x9E3779B1u) >> (32 - cache_log2)) << 3);
+                uint32_t owner = lds32(slot);
+                if (owner == 0) {
+                    asm volatile("atom.shared.cas.b32 %0, [%1], 0, %2;" : "=r"(owner) : "r"(slot), "r"(key) : "memory");
+                    if (owner == 0) owner = key;
+                }
+                if (owner == key) red_shared_inc(slot + 4);
+                else atomicAdd(p.def[d].hist + (size_t)c * p.def[d].num_states + s, 1ull);
+            }
         }
     };
 
@@ -462,6 +481,17 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     if (p.fuse) emit_publish<D>(p, etb, tot);
 
     // ---- flush the multiplicity bins: bin (s,c) of def d -> dense global histogram [c*S + s] -------------------------------
+    if (HM != (int)HIST_SMEM) {
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint32_t S = p.def[d].num_states;
+            for (uint32_t i = threadIdx.x; i < (1u << cache_log2); i += blockDim.x) {
+                const uint32_t key = lds32(hist_s[d] + i * 8), v = lds32(hist_s[d] + i * 8 + 4);
+                if (key && v) atomicAdd(p.def[d].hist + (size_t)((key - 1) & 255u) * S + ((key - 1) >> 8), (unsigned long long)v);
+            }
+        }
+    }
     if (HM == (int)HIST_SMEM) {
         __syncthreads();
 #pragma unroll
