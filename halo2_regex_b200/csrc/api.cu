@@ -78,12 +78,11 @@ struct b2r_config {
     // staging for the host-pointer entry point
     DevBuf ws_bytes, ws_offsets, ws_cols;
     cudaStream_t host_stream = nullptr;
-    cudaStream_t fill_stream = nullptr;   // zero-fill of the sparse columns, overlapping the walk
     cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host entry point: H2D / D2H copies overlapping the kernels
     static constexpr int MAX_SLICES = 8;
     cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
     BatchCounters* h_slices = nullptr;    // pinned: the counters of every slice of a host batch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr;
 };
 
 namespace {
@@ -188,7 +187,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     { const char* dbg = getenv("B2R_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
-    { const char* f = getenv("B2R_FUSE"); p.fuse = (f && f[0] == '0') ? 0u : (f && f[0] == '2') ? 0u : 1u; p.prefilled = (f && f[0] == '2') ? 1u : 0u; }   // testing hooks: 0 separate emit_kernel, 2 + memset on a side stream
+    { const char* f = getenv("B2R_FUSE"); p.fuse = (f && f[0] == '0') ? 0u : 1u; }   // testing hook: B2R_FUSE=0 runs emit_kernel as its own launch
     p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;
@@ -343,14 +342,12 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         int rc = upload_tables(c.get());
         if (rc) return rc;
         CUDA_TRY(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->fill_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
         for (auto& e : c->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaMallocHost((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     }
     *out = c.release();
@@ -366,14 +363,12 @@ void b2r_config_free(b2r_config* c) {
         for (auto& b : c->ws_states) b.release();
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
-        if (c->fill_stream) cudaStreamDestroy(c->fill_stream);
         if (c->in_stream) cudaStreamDestroy(c->in_stream);
         if (c->out_stream) cudaStreamDestroy(c->out_stream);
         for (auto& e : c->ev_in) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_done) if (e) cudaEventDestroy(e);
         if (c->h_slices) cudaFreeHost(c->h_slices);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-        if (c->ev_join) cudaEventDestroy(c->ev_join);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     }
     delete c;
@@ -435,26 +430,12 @@ static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_
         if ((rc = plan_walk(p, wide, c->force_table_mode, c->force_hist_mode))) return rc;
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
-    if (n && p.prefilled) {   // zero the sparse columns on the side stream while the walk runs
-        CUDA_TRY(cudaEventRecord(c->ev_fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(c->fill_stream, c->ev_fork, 0));
-        auto zero = [&](void* ptr, size_t bytes) { return ptr ? cudaMemsetAsync(ptr, 0, bytes, c->fill_stream) : cudaSuccess; };
-        for (uint32_t d = 0; d < c->n_defs; d++) {
-            CUDA_TRY(zero(o->substr_ids[d], n * o->row_pitch));
-            CUDA_TRY(zero(o->start_enable[d], n * o->bitmap_pitch));
-            CUDA_TRY(zero(o->end_enable[d], n * o->bitmap_pitch));
-        }
-        CUDA_TRY(zero(o->masked_chars, n * o->row_pitch));
-        CUDA_TRY(zero(o->masked_substr_ids, n * o->row_pitch));
-        CUDA_TRY(cudaEventRecord(c->ev_join, c->fill_stream));
-    }
     if (n) {
         if ((rc = launch_walk(p, wide, st, nullptr))) return rc;
         c->last_launches++;
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
     if (n && !p.fuse) {
-        if (p.prefilled) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
         if ((rc = launch_emit(p, wide, st, nullptr))) return rc;
         c->last_launches++;
     }

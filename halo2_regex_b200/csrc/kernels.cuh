@@ -75,7 +75,7 @@ struct WalkParams {
     uint32_t segment_mode;           // 1: the "strings" are consecutive chunks of ONE long string (long.cuh): string j starts in
                                      //    init_states[j], stores only its own rows (the last one also the final state), no emit stage
     uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
-    uint32_t prefilled;              // 1: the sparse columns were zeroed before emit_kernel (memset on a side stream, overlapping the walk)
+    uint32_t prefilled;              // 1: the sparse columns were zeroed before the emit stage runs (long-string path: memset)
     uint32_t debug;                  // timing experiments only (B2R_DEBUG env): emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status
 };
 
