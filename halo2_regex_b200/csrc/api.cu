@@ -652,6 +652,9 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
         off_entry[d] = slot(nodes * 2);
         off_states[d] = o->states[d] ? 0 : slot(align_up(M, 16) * (wide ? 2 : 1) + 64);
     }
+    uint32_t max_s1 = 0;
+    for (uint32_t d = 0; d < c->n_defs; d++) max_s1 = std::max(max_s1, c->packed[d].num_states + 1);
+    const size_t off_uniq = slot((size_t)n_chunks * 4 * 2), off_nuniq = slot(n_chunks), off_which = slot((size_t)n_chunks * max_s1);
     if ((rc = c->ws_long.reserve(need))) return rc;
     unsigned char* ws = (unsigned char*)c->ws_long.p;
     uint64_t* d_offsets = (uint64_t*)(ws + off_offsets);
@@ -662,6 +665,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     LongParams lp;
     memset(&lp, 0, sizeof lp);
     lp.bytes = d_bytes; lp.len = len; lp.n_chunks = n_chunks; lp.n_defs = c->n_defs; lp.offsets = d_offsets;
+    lp.uniq = (uint16_t*)(ws + off_uniq); lp.n_uniq = ws + off_nuniq; lp.which = ws + off_which;
     for (uint32_t d = 0; d < c->n_defs; d++) {
         lp.def[d].byte_class = c->dev[d].byte_class; lp.def[d].trans = c->dev[d].trans;
         lp.def[d].num_states = c->packed[d].num_states; lp.def[d].first_state = c->packed[d].first_state;

@@ -15,22 +15,82 @@ __global__ void long_offsets_kernel(uint64_t* offsets, uint32_t n_chunks, uint64
     if (i <= n_chunks) { const uint64_t o = (uint64_t)i * LONG_CHUNK; offsets[i] = o < len ? o : len; }
 }
 
-// f_k[s] for every chunk k and state s in [0, S]; S is the trap state (an invalid transition, sticky)
-__global__ void __launch_bounds__(256) long_maps_kernel(const __grid_constant__ LongParams p, uint32_t d) {
-    const uint32_t S = p.def[d].num_states, S1 = S + 1;
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)p.n_chunks * S1) return;
-    const uint32_t k = (uint32_t)(t / S1);
-    uint32_t s = (uint32_t)(t % S1);
-    const uint64_t a = (uint64_t)k * LONG_CHUNK;
-    const uint64_t b = a + LONG_CHUNK < p.len ? a + LONG_CHUNK : p.len;
+// f_k[s] for every chunk k and state s in [0, S]; S is the trap state (an invalid transition, sticky).
+// The S+1 walks of a chunk merge quickly (the shipped DFAs are down to <= 2 distinct images after a few bytes), so the
+// transition vector is computed in three steps:
+//   head   thread per (chunk, state): walk the first LONG_HEAD bytes                       -> maps[k][s] = image after the head
+//   dedupe thread per chunk: the distinct images (at most LONG_MAXU, else the chunk is marked wide) and, per state, which one
+//   tail   thread per (chunk, distinct image): walk the rest of the chunk; wide chunks: thread per (chunk, state)
+//   gather thread per (chunk, state): maps[k][s] = tail result of its image
+constexpr uint32_t LONG_HEAD = 64;
+constexpr uint32_t LONG_MAXU = 4;
+
+__device__ __forceinline__ uint32_t long_walk(const LongParams& p, uint32_t d, uint32_t s, uint64_t a, uint64_t b) {
+    const uint32_t S = p.def[d].num_states;
     const uint8_t* cls = p.def[d].byte_class;
     const uint32_t* tr = p.def[d].trans;
     for (uint64_t i = a; i < b && s < S; i++) {
         const uint32_t e = __ldg(tr + (uint32_t)__ldg(cls + __ldg(p.bytes + i)) * S + s);
         s = (e & ENT_INVALID) ? S : (e & ENT_NEXT_MASK);
     }
-    p.def[d].maps[t] = (uint16_t)s;
+    return s;
+}
+__device__ __forceinline__ void long_chunk_range(const LongParams& p, uint32_t k, uint64_t& a, uint64_t& mid, uint64_t& b) {
+    a = (uint64_t)k * LONG_CHUNK;
+    b = a + LONG_CHUNK < p.len ? a + LONG_CHUNK : p.len;
+    mid = a + LONG_HEAD < b ? a + LONG_HEAD : b;
+}
+
+__global__ void __launch_bounds__(256) long_maps_head_kernel(const __grid_constant__ LongParams p, uint32_t d) {
+    const uint32_t S1 = p.def[d].num_states + 1;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)p.n_chunks * S1) return;
+    uint64_t a, mid, b;
+    long_chunk_range(p, (uint32_t)(t / S1), a, mid, b);
+    p.def[d].maps[t] = (uint16_t)long_walk(p, d, (uint32_t)(t % S1), a, mid);
+}
+
+// uniq[k][0..LONG_MAXU): the distinct images of chunk k (count in n_uniq[k]; LONG_MAXU+1 = more than that: wide chunk);
+// which[k*S1 + s]: index of the image of state s
+__global__ void __launch_bounds__(256) long_dedupe_kernel(const __grid_constant__ LongParams p, uint32_t d, uint16_t* uniq, uint8_t* n_uniq, uint8_t* which) {
+    const uint32_t S1 = p.def[d].num_states + 1;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.n_chunks) return;
+    const uint16_t* img = p.def[d].maps + (size_t)k * S1;
+    uint16_t u[LONG_MAXU];
+    uint32_t n = 0;
+    for (uint32_t s = 0; s < S1 && n <= LONG_MAXU; s++) {
+        const uint16_t v = img[s];
+        uint32_t j = 0;
+        while (j < n && u[j] != v) j++;
+        if (j == n) { if (n < LONG_MAXU) u[n] = v; n++; }
+        if (n <= LONG_MAXU) which[(size_t)k * S1 + s] = (uint8_t)j;
+    }
+    n_uniq[k] = (uint8_t)n;
+    for (uint32_t j = 0; j < LONG_MAXU; j++) uniq[(size_t)k * LONG_MAXU + j] = j < n ? u[j] : 0;
+}
+
+// narrow chunks: thread per (chunk, distinct image) walks the rest of the chunk; result overwrites uniq
+__global__ void __launch_bounds__(256) long_maps_tail_kernel(const __grid_constant__ LongParams p, uint32_t d, uint16_t* uniq, const uint8_t* n_uniq) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)p.n_chunks * LONG_MAXU) return;
+    const uint32_t k = (uint32_t)(t / LONG_MAXU), j = (uint32_t)(t % LONG_MAXU);
+    if (j >= n_uniq[k] || n_uniq[k] > LONG_MAXU) return;
+    uint64_t a, mid, b;
+    long_chunk_range(p, k, a, mid, b);
+    uniq[t] = (uint16_t)long_walk(p, d, uniq[t], mid, b);
+}
+
+// thread per (chunk, state): narrow chunks gather the result of their image, wide chunks walk the rest themselves
+__global__ void __launch_bounds__(256) long_maps_gather_kernel(const __grid_constant__ LongParams p, uint32_t d, const uint16_t* uniq, const uint8_t* n_uniq, const uint8_t* which) {
+    const uint32_t S1 = p.def[d].num_states + 1;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)p.n_chunks * S1) return;
+    const uint32_t k = (uint32_t)(t / S1);
+    if (n_uniq[k] <= LONG_MAXU) { p.def[d].maps[t] = uniq[(size_t)k * LONG_MAXU + which[t]]; return; }
+    uint64_t a, mid, b;
+    long_chunk_range(p, k, a, mid, b);
+    p.def[d].maps[t] = (uint16_t)long_walk(p, d, p.def[d].maps[t], mid, b);
 }
 
 // level l+1 map i = composition of its (up to 64) children at level l; thread per (node, state)
@@ -173,8 +233,14 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
     for (uint32_t d = 0; d < lp.n_defs; d++) {
         const uint32_t S1 = lp.def[d].num_states + 1;
         const uint64_t threads = (uint64_t)lp.n_chunks * S1;
-        long_maps_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d);
-        LAUNCH_CHECK("long_maps_kernel"); (*launches)++;
+        long_maps_head_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d);
+        LAUNCH_CHECK("long_maps_head_kernel"); (*launches)++;
+        long_dedupe_kernel<<<(lp.n_chunks + 255) / 256, 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
+        LAUNCH_CHECK("long_dedupe_kernel"); (*launches)++;
+        long_maps_tail_kernel<<<(unsigned)(((uint64_t)lp.n_chunks * LONG_MAXU + 255) / 256), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq);
+        LAUNCH_CHECK("long_maps_tail_kernel"); (*launches)++;
+        long_maps_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
+        LAUNCH_CHECK("long_maps_gather_kernel"); (*launches)++;
         // up the tree
         std::vector<uint32_t> n_level{lp.n_chunks};
         std::vector<size_t> off_level{0};

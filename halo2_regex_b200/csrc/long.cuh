@@ -1,8 +1,8 @@
 // Long-string path (b2r_match_long; BASELINE config "single 64 MiB string"): ONE string of `len` bytes, M = len + 1 rows.
 //
 // The walk is a dependent chain over the whole string, so it is cut into chunks of LONG_CHUNK bytes:
-//   1. long_maps_kernel      every chunk's transition vector f_k : S -> S (state after the chunk for EVERY state before
-//                            it), one thread per (chunk, state);
+//   1. long_maps_*_kernel    every chunk's transition vector f_k : S -> S (state after the chunk for EVERY state before
+//                            it): all states over a 64-byte head, then only the distinct images over the rest;
 //   2. long_compose_kernel   parallel-prefix composition, 64-ary tree: level l+1 map i = f of its 64 children composed;
 //      long_propagate_kernel back down the tree: the state in which every node starts, from first_state at the root;
 //   3. walk_kernel           in segment mode: chunk k is "string" k, starts in its now-known entry state, writes its slice
@@ -36,6 +36,10 @@ struct LongParams {
         uint16_t* entry;                 // all levels back to back: entry state of every node
     } def[B2R_MAX_DEFS];
     uint64_t* offsets;                   // [n_chunks + 1]
+    // scratch of the transition-vector pass (reused by every def): distinct images per chunk, their count, image index per state
+    uint16_t* uniq;                      // [n_chunks][4]
+    uint8_t* n_uniq;                     // [n_chunks]
+    uint8_t* which;                      // [n_chunks][max S + 1]
 };
 
 // host-callable (long.cu)
