@@ -7,4 +7,4 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
     python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/r1_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name regex:walk_kernel --launch-skip 3 --launch-count 1 \
     -o gpurun_out/r1_walk_kernel -f python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/r1_full.log 2>&1
-tail -2 gpurun_out/r1_launches_bench.log gpurun_out/r1_full.log
+tail -n 2 gpurun_out/r1_launches_bench.log; tail -n 2 gpurun_out/r1_full.log
