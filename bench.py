@@ -222,11 +222,11 @@ def main():
         step()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if rank == 0:
+        sampler.start()          # before the barrier: NVML start-up on rank 0 must not delay its first step (the others would wait for it)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()      # `ncu --profile-from-start off` lists exactly the launches of the timed region
     t_begin.record(stream)
