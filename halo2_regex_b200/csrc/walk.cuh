@@ -65,7 +65,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory"); }
-// 16-byte async copy global -> shared; copies src_bytes (0 or 16) and zero-fills the rest
+// 16-byte async copy global -> shared; copies src_bytes (0..16) and zero-fills the rest
 __device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
@@ -286,8 +286,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             const uint32_t cbase = chunk * DCH;
             const uint32_t dst = in_s + (chunk & 1) * (32 * PITCH) + kv * 16;
 #pragma unroll
-            for (int i = 0; i < VPR; i++) cp_async16(dst + (r0 + (32 / VPR) * i) * PITCH, in_ptr[i] + cbase, cbase < in_left[i] ? 16u : 0u);
-            if (any_shift) cp_async16(in_s + (chunk & 1) * (32 * PITCH) + lane * PITCH + DCH, my_tail + cbase, cbase < my_tail_left ? 16u : 0u);
+            // src-size = the bytes of the string that are left (at most 16): nothing past the end of the string is read
+            for (int i = 0; i < VPR; i++) cp_async16(dst + (r0 + (32 / VPR) * i) * PITCH, in_ptr[i] + cbase, cbase < in_left[i] ? min(16u, in_left[i] - cbase) : 0u);
+            if (any_shift) cp_async16(in_s + (chunk & 1) * (32 * PITCH) + lane * PITCH + DCH, my_tail + cbase, cbase < my_tail_left ? min(16u, my_tail_left - cbase) : 0u);
             cp_async_commit();
         };
         stage(0);
