@@ -1,0 +1,33 @@
+"""The compiled-language host mirror of the reference API (include/b2r.hpp, C++ on top of the C ABI): it builds here on CPU,
+and on the GPU box the reference's own test cases (tests/cpp/test_reference_cases.cpp) run through it."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_reference_cases.cpp")
+LIBDIR = os.path.join(ROOT, "halo2_regex_b200")
+
+
+def _build(tmp_path):
+    exe = os.path.join(str(tmp_path), "test_reference_cases")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe, SRC, "-L", LIBDIR, "-lb2r", f"-Wl,-rpath,{LIBDIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_mirror_builds_and_refuses_to_run_without_a_gpu(tmp_path):
+    import torch
+    exe = _build(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "defs")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout      # fails loudly, does not fall back
+
+
+@pytest.mark.gpu
+def test_reference_cases_through_the_cpp_host(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "defs")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all reference cases pass" in r.stdout, r.stdout + r.stderr
