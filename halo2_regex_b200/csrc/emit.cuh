@@ -517,10 +517,16 @@ struct TileEmitter {
                     if (fin[d] == p.def[d].accepted_state) flags |= B2R_ST_ACCEPTED(d);
                 if (p.records && r_nrec > p.max_records) flags |= B2R_ST_RECORDS_TRUNCATED;
                 if (p.compact_bytes && r_ncmp > p.compact_pitch) flags |= B2R_ST_COMPACT_TRUNCATED;
-                if (p.status) {
-                    b2r_string_status st = {};
-                    st.flags = flags; st.err_pos = NO_POS; st.n_records = r_nrec; st.n_compact = r_ncmp;
-                    p.status[jl] = st;
+                if (p.status) {   // 32 bytes per string: two 16-byte stores when the array is 16-byte aligned (2 x 32 sectors per warp, not 8 x 32)
+                    if ((reinterpret_cast<uintptr_t>(p.status) & 15) == 0) {
+                        uint4* q = reinterpret_cast<uint4*>(p.status + jl);
+                        q[0] = make_uint4(flags, NO_POS, 0u, 0u);        // flags, err_pos, err_state, err_byte/err_def/reserved0
+                        q[1] = make_uint4(r_nrec, r_ncmp, 0u, 0u);       // n_records, n_compact, reserved1[2]
+                    } else {
+                        b2r_string_status st = {};
+                        st.flags = flags; st.err_pos = NO_POS; st.n_records = r_nrec; st.n_compact = r_ncmp;
+                        p.status[jl] = st;
+                    }
                 }
                 tot.pad_rows += M - Ll; tot.n_ok++; tot.n_overlap += (r_flags & B2R_ST_OVERLAP) ? 1u : 0u;
             }
