@@ -119,7 +119,7 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
     const bool inplace = p.n_defs == 1 && state_bytes == 1;
     L.st_off = 2 * 32 * WALK_PITCH;
     L.stash_off = L.st_off + (inplace ? 0u : p.n_defs * 32 * (WALK_DCH * state_bytes + 16));
-    L.per_warp = L.stash_off + (p.fuse ? 32u * 16u * (1u + p.n_defs * state_bytes) : 0u);
+    L.per_warp = L.stash_off + ((p.fuse && p.n_defs == 1) ? 32u * 16u * (1u + p.n_defs * state_bytes) : 0u);   // stash: one def only (else the warps matter more)
     L.align = al;
     return L;
 }
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 const uint32_t gi = (cbase >> 4) + g;                   // granule index
                 if (acc & 1u) {
                     fm |= 1u << (gi & 31);
-                    if (p.fuse && stash_g == NO_POS) {                  // keep the first flagged granule of my string for the emit stage
+                    if (D == 1 && p.fuse && stash_g == NO_POS) {        // keep the first flagged granule of my string for the emit stage
                         stash_g = gi;
                         sts128(stash_s, w[0], w[1], w[2], w[3]);
 #pragma unroll
