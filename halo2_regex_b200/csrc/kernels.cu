@@ -54,7 +54,7 @@ static int device_limits(int* n_sm, int* max_smem) {
     return B2R_OK;
 }
 
-static constexpr int MIN_WARPS_REPL = 8;   // below this the replicated tables are not worth the lost occupancy
+static constexpr int MIN_WARPS_REPL = 12;  // below this the replicated tables are not worth the lost occupancy (measured on the two-def set)
 
 // Picks where the walk tables and the multiplicity bins live.  Preference: replicated tables + shared bins with as many
 // warps as possible; then a single copy of the tables; then global tables.  Bins go to shared memory whenever they fit.
