@@ -396,3 +396,17 @@ def test_host_entry_point_slices():
     cfg, g, o = _both("test1", 61, bad)
     import halo2_regex_b200 as H
     assert g.status["flags"][9000] & H._abi.B2R_ST_INVALID_TRANSITION and g.status["flags"][17000] & H._abi.B2R_ST_INVALID_TRANSITION
+
+
+@pytest.mark.parametrize("set_name,M", [("regex1", 257), ("test1", 130), ("regex3_k3", 513), ("three", 100), ("example", 64)])
+def test_fuzz_many_strings(set_name, M):
+    """Differential fuzz at a larger count: 30 000 random ragged strings (snippets of the regexes spliced into alphabet noise,
+    some with bytes outside the alphabet) per definition set, every column against the oracle."""
+    rng = random.Random(zlib.crc32(f"{set_name}/{M}".encode()))
+    strings = _random_strings(rng, 30000, M - 1, SNIPPETS)
+    if set_name != "example":            # a few invalid bytes: the batch fails like the reference, per-string statuses must still agree
+        for k in range(0, 30000, 7919):
+            s = bytearray(strings[k] or b"x")
+            s[rng.randrange(len(s))] = rng.choice([0, 1, 127, 200, 255])
+            strings[k] = bytes(s)
+    _both(set_name, M, strings)
