@@ -144,7 +144,7 @@ int upload_tables(b2r_config* c) {
     }
     CUDA_TRY(cudaMalloc((void**)&c->d_batch_status, sizeof(b2r_batch_status)));
     if (const char* tm = getenv("B2R_TABLE_MODE"))
-        c->force_table_mode = !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
+        c->force_table_mode = !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "plain16") ? (int)TABLE_PLAIN16 : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
     if (const char* hm = getenv("B2R_HIST_MODE"))
         c->force_hist_mode = !strcmp(hm, "smem") ? (int)HIST_SMEM : !strcmp(hm, "global") ? (int)HIST_GLOBAL : -1;
     return B2R_OK;

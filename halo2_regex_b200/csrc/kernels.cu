@@ -68,7 +68,7 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
         if (tm != TABLE_GLOBAL) {
             const uint32_t stride = walk_stride(tm);
             for (uint32_t d = 0; d < p.n_defs; d++)
-                if ((uint64_t)p.def[d].padded_states * stride > 65536u) return false;   // entry bits [15:2] hold next*stride/4
+                if ((uint64_t)p.def[d].padded_states * stride > 65536u) return false;   // the entry's low bits hold next*stride
         }
         uint64_t bins = 0;
         for (uint32_t d = 0; d < p.n_defs; d++) bins += (uint64_t)(p.def[d].num_states + 1) * 1024u;
@@ -86,17 +86,25 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
         p.hist_cache_log2 = 8;
         return false;
     };
-    static const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {TABLE_PLAIN, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL},
-                                       {TABLE_PLAIN, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
+    // preference: replicated tables + shared bins; a single copy; 16-bit entries (large DFAs); bins behind the cache; global
+    // tables.  A placement is taken when at least `need` warps fit next to it.
+    // (a single copy of 32-bit entries beyond 48 KB: the 16-bit entries go first — more warps and a larger bin cache fit;
+    //  measured 2.2x on the 1023-state DFA)
+    uint64_t plain_bytes = 0;
+    for (uint32_t d = 0; d < p.n_defs; d++) plain_bytes += (uint64_t)p.def[d].num_classes * p.def[d].padded_states * 4;
+    const uint32_t P32 = plain_bytes > 48 * 1024 ? TABLE_PLAIN16 : TABLE_PLAIN, P16 = plain_bytes > 48 * 1024 ? TABLE_PLAIN : TABLE_PLAIN16;
+    const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P32, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P32, HIST_GLOBAL},
+                                 {P16, HIST_SMEM}, {P16, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
     for (const auto& o : order) {
         if (force_table_mode >= 0 && (uint32_t)force_table_mode != o[0]) continue;   // testing hooks: honoured when they fit
         if (force_hist_mode >= 0 && (uint32_t)force_hist_mode != o[1]) continue;
         if (fits(o[0], o[1], 4)) return B2R_OK;
     }
-    for (const auto& o : order) {
-        const int need = o[0] == TABLE_REPL ? MIN_WARPS_REPL : 4;
-        if (fits(o[0], o[1], need)) return B2R_OK;
-    }
+    for (const int need : {MIN_WARPS_REPL, 4})
+        for (const auto& o : order) {
+            if (o[0] == TABLE_GLOBAL && need != 4) continue;                       // global tables: the last resort
+            if (fits(o[0], o[1], o[0] == TABLE_REPL ? MIN_WARPS_REPL : need)) return B2R_OK;
+        }
     set_error("walk_kernel: no table placement fits in shared memory");
     return B2R_ERR_UNSUPPORTED;
 }

@@ -82,6 +82,7 @@ struct WalkParams {
 constexpr uint32_t TABLE_REPL = 0;   // shared memory, one copy of every entry per bank (stride 128 B): conflict-free lookups
 constexpr uint32_t TABLE_PLAIN = 1;  // shared memory, one copy (stride 4 B)
 constexpr uint32_t TABLE_GLOBAL = 2; // global memory (L1/L2)
+constexpr uint32_t TABLE_PLAIN16 = 3; // shared memory, one copy of 16-bit entries (next << 1 | rare): half the size, for large DFAs
 // HIST_SMEM: dense bins [state][byte] in shared memory.  HIST_GLOBAL (bins too large for that): 64-bit atomics on the global
 // bins, behind a shared-memory cache of (key, count) slots that absorbs the hot (byte, state) pairs.
 constexpr uint32_t HIST_NONE = 0, HIST_SMEM = 1, HIST_GLOBAL = 2;

@@ -74,7 +74,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- shared-memory layout, computed identically by the launcher and the kernel ---------------------------------------------
-__host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : 4u; }
+// bytes between consecutive table entries; class-table entries are 4 bytes (128 when replicated)
+__host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : table_mode == TABLE_PLAIN16 ? 2u : 4u; }
+__host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : 4u; }
 __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
 struct WalkLayout {
@@ -101,7 +103,7 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
         }
         cur = walk_align_up(cur, 128);
         L.cls = cur;
-        cur += 256 * stride;
+        cur += 256 * walk_cls_stride(p.table_mode);
     }
     if (p.hist_mode == HIST_SMEM)
         for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
@@ -128,7 +130,7 @@ __host__ __device__ inline size_t walk_smem_bytes(const WalkParams& p, uint32_t 
     return (size_t)L.align + L.tiles + (size_t)warps * L.per_warp;   // + align: the dynamic base is only 16-byte aligned
 }
 
-// TM: TABLE_REPL, TABLE_PLAIN or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
+// TM: TABLE_REPL, TABLE_PLAIN, TABLE_PLAIN16 or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
 template <int D, typename ST, int TM, int HM>
 __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_constant__ WalkParams p) {
     constexpr int DCH = WALK_DCH, PITCH = WALK_PITCH;
@@ -143,7 +145,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 
     const WalkLayout lay = walk_layout(p, SB);
     const uint32_t base_s = (smem_u32(dsmem) + lay.align - 1) & ~(lay.align - 1);
-    constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_PLAIN ? 4u : 0u;
+    constexpr bool E16 = TM == (int)TABLE_PLAIN16;                       // 16-bit entries: next << 1 | rare (else next << 16 | next * stride | rare)
+    constexpr uint32_t NSH = E16 ? 1u : 16u;                            // entry >> NSH = the state
+    constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
+    constexpr uint32_t cstride = TM == (int)TABLE_REPL ? 128u : 4u;       // class-table entry stride
     const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : 0u;
 
     // ---- stage the tables ----------------------------------------------------------------------------------------------
@@ -156,7 +161,8 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             for (uint32_t i = threadIdx.x; i < (n << csh); i += blockDim.x) {
                 const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u);
                 const uint32_t e = __ldg(p.def[d].hot + idx);
-                sts32(t0 + idx * stride + l * 4, e | ((e >> 16) * stride));
+                if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + idx * 2), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
+                else sts32(t0 + idx * stride + l * 4, e | ((e >> 16) * stride));
             }
         }
         for (uint32_t i = threadIdx.x; i < (256u << csh); i += blockDim.x) {
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
                 for (int d = 0; d < D; d++) v |= (uint32_t)__ldg(p.def[d].byte_class + c) << (8 * d);
             }
-            sts32(base_s + lay.cls + c * stride + l * 4, v);
+            sts32(base_s + lay.cls + c * cstride + l * 4, v);
         }
     }
     if (HM == (int)HIST_SMEM) {
@@ -215,19 +221,20 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     auto lookup = [&](int d, uint32_t cur, uint32_t c, uint32_t cent) -> uint32_t {
         if (SMEM_TAB) {
             const uint32_t row = (D == 1) ? cent : tabl[d] + ((cent >> (8 * d)) & 0xFFu) * rowb[d];
+            if (E16) { uint32_t e; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((cur & 0xFFFEu) | row)); return e; }
             return lds32((cur & 0xFFFCu) | row);
         } else {
             const uint32_t k = __ldg(p.def[d].byte_class + c);
-            return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> 16));
+            return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> NSH));
         }
     };
     const uint32_t cache_log2 = p.hist_cache_log2;
     auto count = [&](int d, uint32_t cur, uint32_t c) {
-        if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> 16) << 8) | c) * 4);
+        if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> NSH) << 8) | c) * 4);
         else {
             // bin cache: slot = {key, count}; a slot is claimed by the first key that hashes to it and never changes owner,
             // every other key of that slot goes to the global bins (exact either way)
-            const uint32_t s = cur >> 16;
+            const uint32_t s = cur >> NSH;
             if (s < p.def[d].num_states) {
                 const uint32_t key = ((s << 8) | c) + 1u;
                 const uint32_t slot = hist_s[d] + (((key * 0x9E3779B1u) >> (32 - cache_log2)) << 3);
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t f = (p.def[d].init_states && valid) ? (uint32_t)p.def[d].init_states[idx] : p.def[d].first_state;
-            cur[d] = (f << 16) | (f * stride);
+            cur[d] = E16 ? (f << 1) : (f << 16) | (f * stride);
         }
 
         // staging geometry
@@ -359,11 +366,11 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         for (int j = 0; j < 4; j++) {
                             const uint32_t c = prmt(w[q], 0u, 0x4440u + j);
                             uint32_t cent = 0;
-                            if (SMEM_TAB) cent = lds32(cls_lane_s + c * stride);
+                            if (SMEM_TAB) cent = lds32(cls_lane_s + c * cstride);
 #pragma unroll
                             for (int d = 0; d < D; d++) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);
-                                if (HM == (int)HIST_SMEM && SB == 1)     // bin index (state << 8 | byte) in one byte permute
+                                if (HM == (int)HIST_SMEM && SB == 1 && !E16)   // bin index (state << 8 | byte) in one byte permute
                                     red_shared_inc(hist_s[d] + prmt(cur[d], w[q], 0x3324u + j) * 4);
                                 else count(d, cur[d], c);
                                 before[d][j] = cur[d];
@@ -374,7 +381,13 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         for (int d = 0; d < D; d++) {
                             acc |= before[d][1] | before[d][2];           // entries of rows 4q, 4q+1 (3-input LOP3s)
                             acc |= before[d][3] | cur[d];                 // rows 4q+2, 4q+3
-                            if (SB == 1) {                                // state bytes (entry byte 2) of four rows into one word
+                            if (E16) {                                    // 16-bit entries: the state is entry >> 1
+                                if (SB == 1) pk[d][q] = (before[d][0] >> 1) | ((before[d][1] >> 1) << 8) | ((before[d][2] >> 1) << 16) | ((before[d][3] >> 1) << 24);
+                                else {
+                                    pk[d][q * 2] = (before[d][0] >> 1) | ((before[d][1] >> 1) << 16);
+                                    pk[d][q * 2 + 1] = (before[d][2] >> 1) | ((before[d][3] >> 1) << 16);
+                                }
+                            } else if (SB == 1) {                         // state bytes (entry byte 2) of four rows into one word
                                 const uint32_t lo = prmt(before[d][0], before[d][1], 0x4462u), hi = prmt(before[d][2], before[d][3], 0x4462u);
                                 pk[d][q] = prmt(lo, hi, 0x5410u);
                             } else {
@@ -396,10 +409,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         const uint32_t c = v0 & 0xFFu;
                         v0 = __funnelshift_r(v0, v1, 8); v1 = __funnelshift_r(v1, v2, 8); v2 = __funnelshift_r(v2, v3, 8); v3 >>= 8;
                         uint32_t cent = 0;
-                        if (SMEM_TAB && pos < L) cent = lds32(cls_lane_s + c * stride);
+                        if (SMEM_TAB && pos < L) cent = lds32(cls_lane_s + c * cstride);
 #pragma unroll
                         for (int d = 0; d < D; d++) {
-                            const uint32_t stv = (pos <= L) ? (cur[d] >> 16) : p.def[d].num_states;   // state, final state, then dummy
+                            const uint32_t stv = (pos <= L) ? (cur[d] >> NSH) : p.def[d].num_states;   // state, final state, then dummy
                             if (pos < L) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);
                                 count(d, cur[d], c);
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             __syncwarp();                                                 // ... and so have those of the other lanes
             uint32_t fin[D];
 #pragma unroll
-            for (int d = 0; d < D; d++) fin[d] = cur[d] >> 16;
+            for (int d = 0; d < D; d++) fin[d] = cur[d] >> NSH;
             emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true, stash_g, stash_s);
         }
     }

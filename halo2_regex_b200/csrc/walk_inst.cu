@@ -26,21 +26,27 @@ int launch_walk_d(const WalkParams& p, bool wide, size_t smem, int grid, int blo
 template <>
 int launch_walk_d<B2R_INST_D>(const WalkParams& p, bool wide, size_t smem, int grid, int block, cudaStream_t st) {
     constexpr int D = B2R_INST_D;
-    const bool gtab = p.table_mode == TABLE_GLOBAL, repl = p.table_mode == TABLE_REPL;
+    const uint32_t tm = p.table_mode;
     const bool shist = p.hist_mode == HIST_SMEM;
     if (wide) {   // 2-byte states: more than 255 states, the bins never fit in shared memory
         if (shist) { set_error("walk_kernel: shared-memory bins with 2-byte states"); return B2R_ERR_UNSUPPORTED; }
-        if (gtab) return launch_walk_one<D, uint16_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st);
-        return repl ? launch_walk_one<D, uint16_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st)
-                    : launch_walk_one<D, uint16_t, TABLE_PLAIN, HIST_GLOBAL>(p, smem, grid, block, st);
+        switch (tm) {
+            case TABLE_REPL: return launch_walk_one<D, uint16_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+            case TABLE_PLAIN: return launch_walk_one<D, uint16_t, TABLE_PLAIN, HIST_GLOBAL>(p, smem, grid, block, st);
+            case TABLE_PLAIN16: return launch_walk_one<D, uint16_t, TABLE_PLAIN16, HIST_GLOBAL>(p, smem, grid, block, st);
+            default: return launch_walk_one<D, uint16_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st);
+        }
     }
-    if (gtab) {
+    if (tm == TABLE_GLOBAL) {
         if (shist) { set_error("walk_kernel: shared-memory bins with global tables"); return B2R_ERR_UNSUPPORTED; }
         return launch_walk_one<D, uint8_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st);
     }
-    if (repl)
+    if (tm == TABLE_REPL)
         return shist ? launch_walk_one<D, uint8_t, TABLE_REPL, HIST_SMEM>(p, smem, grid, block, st)
                      : launch_walk_one<D, uint8_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+    if (tm == TABLE_PLAIN16)
+        return shist ? launch_walk_one<D, uint8_t, TABLE_PLAIN16, HIST_SMEM>(p, smem, grid, block, st)
+                     : launch_walk_one<D, uint8_t, TABLE_PLAIN16, HIST_GLOBAL>(p, smem, grid, block, st);
     return shist ? launch_walk_one<D, uint8_t, TABLE_PLAIN, HIST_SMEM>(p, smem, grid, block, st)
                  : launch_walk_one<D, uint8_t, TABLE_PLAIN, HIST_GLOBAL>(p, smem, grid, block, st);
 }
