@@ -10,4 +10,6 @@ from .defs import AllstrRegexDef, RegexDefs, RegexParseError, SubstrRegexDef  # 
 from .regex import (AssignedRegexResult, DeviceOutputs, InvalidTransitionError, RegexVerifyConfig,  # noqa: F401
                     StringTooLongError)
 
+from . import vrm  # noqa: F401,E402  (host-side definition compiler: regex JSON -> lookup text files)
+
 __version__ = "0.1.0"
