@@ -327,6 +327,10 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         if (n_substrs[d]) max_sum += offset + n_substrs[d] - 1;
         offset += n_substrs[d];  // src/table.rs:197
     }
+    // one storage width for every state column of the config: 2 bytes as soon as one def has a dummy state > 255
+    bool any_wide = false;
+    for (uint32_t d = 0; d < n_defs; d++) any_wide = any_wide || c->packed[d].state_width == 2;
+    if (any_wide) for (uint32_t d = 0; d < n_defs; d++) c->packed[d].state_width = 2;
     if (max_sum > 255) { set_error("sum of the largest substr ids over defs is %llu > 255", (unsigned long long)max_sum); return B2R_ERR_UNSUPPORTED; }
     if (device >= 0) {
         int n_dev = 0;
@@ -417,7 +421,6 @@ static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_
     bool wide = false;
     for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
     for (uint32_t d = 0; d < c->n_defs; d++)
-        if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
     if (n) {
         // walk -> emit hand-over: granule flags, and a scratch state column for every def the caller does not want
         if ((rc = c->ws_fmask.reserve(std::max<size_t>((size_t)p.fm_words * n * 4, 16)))) return rc;
@@ -634,7 +637,6 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     bool wide = false;
     for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
     for (uint32_t d = 0; d < c->n_defs; d++)
-        if (wide && c->packed[d].state_width != 2) { set_error("mixing 1-byte and 2-byte state columns in one config is not supported yet"); return B2R_ERR_UNSUPPORTED; }
     c->last_launches = 0;
     CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
     CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none

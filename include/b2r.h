@@ -102,7 +102,7 @@ void b2r_config_free(b2r_config*);
 uint32_t b2r_config_num_defs(const b2r_config*);
 uint64_t b2r_config_max_chars_size(const b2r_config*);
 int b2r_config_device(const b2r_config*);
-uint32_t b2r_config_state_width(const b2r_config*, uint32_t d);   /* bytes per state: 1 if dummy<=255 else 2 */
+uint32_t b2r_config_state_width(const b2r_config*, uint32_t d);   /* bytes per state, the same for every def: 1 if all dummy<=255 else 2 */
 uint64_t b2r_config_dummy_state(const b2r_config*, uint32_t d);   /* largest_state_val+1 */
 uint32_t b2r_config_substr_id_offset(const b2r_config*, uint32_t d);
 uint32_t b2r_config_num_byte_classes(const b2r_config*, uint32_t d); /* incl. the "no transition" class */

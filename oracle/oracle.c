@@ -470,11 +470,16 @@ static void match_one(const orc_config* c, scratch* t, const uint8_t* characters
     /* assigned_substr_ids (M), assigned_is_start / assigned_is_end (M+1): src/lib.rs:377-385 */
     for (uint64_t i = 0; i <= M; i++) { t->sid_sum[i] = 0; t->is_start_sum[i] = 0; t->is_end_sum[i] = 0; }
 
+    /* storage width of the state columns (a representation choice, include/b2r.h): 2 bytes for every def as soon as
+     * one def has a dummy state > 255 */
+    int wide_states = 0;
+    for (uint32_t d = 0; d < D; d++) wide_states |= c->defs[d].allstr->largest_state_val + 1 > 255;
+
     for (uint32_t d = 0; d < D; d++) {
         const orc_def* df = &c->defs[d];
         const uint64_t dummy = df->allstr->largest_state_val + 1;
         uint8_t* st8 = NULL; uint16_t* st16 = NULL;
-        if (o->states[d]) { if (dummy <= 255) st8 = (uint8_t*)o->states[d] + j * o->row_pitch; else st16 = (uint16_t*)o->states[d] + j * o->row_pitch; }
+        if (o->states[d]) { if (!wide_states) st8 = (uint8_t*)o->states[d] + j * o->row_pitch; else st16 = (uint16_t*)o->states[d] + j * o->row_pitch; }
         uint8_t* sid_out = o->substr_ids[d] ? o->substr_ids[d] + j * o->row_pitch : NULL;
         uint8_t* se_out = o->start_enable[d] ? o->start_enable[d] + j * o->bitmap_pitch : NULL;
         uint8_t* ee_out = o->end_enable[d] ? o->end_enable[d] + j * o->bitmap_pitch : NULL;

@@ -114,7 +114,8 @@ class OracleConfig:
             raise ValueError(f"orc_config_new failed: {rc}")
         self.h, self.n_defs = h, D
         self._keep = (allstr, sub_arrays, subs, ns)
-        self.state_widths = [1 if a.largest_state_val + 1 <= 255 else 2 for a, _ in regex_defs]
+        wide = any(a.largest_state_val + 1 > 255 for a, _ in regex_defs)
+        self.state_widths = [2 if wide else 1] * D
         self.table_num_rows = [lib().orc_table_num_rows(h, d) for d in range(D)]
         self.endpoint_num_rows = [lib().orc_endpoint_num_rows(h, d) for d in range(D)]
 

@@ -277,6 +277,41 @@ def test_wide_state_column():
     assert int(g.states[0].max()) > 255
 
 
+def _wide_allstr(S=300):
+    lines = [f"0\n{S - 1}\n{S - 1}\n"]
+    for s in range(S):
+        for c in range(32, 127):
+            nxt = (s + 1) % S if c == 97 else (s * 7 + c) % S if c % 5 == 0 else s
+            lines.append(f"{s} {nxt} {c}\n")
+    return "".join(lines).encode()
+
+
+@pytest.mark.parametrize("order", ["narrow_first", "wide_first"])
+def test_mixed_state_widths_share_one_width(order):
+    """A def with <= 255 states next to one with more: every state column of the config is stored as u16."""
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    from conftest import read
+    wide = (_wide_allstr(), [b"5\n0\n63\n10 \n13 \n10 11\n11 12\n12 13\n"])
+    narrow = (read("regex1_test_lookup.txt"), [read("substr1_test_lookup.txt")])
+    spec = [narrow, wide] if order == "narrow_first" else [wide, narrow]
+    M = 200
+    cfg = H.RegexVerifyConfig.configure(M, [H.RegexDefs(H.AllstrRegexDef.read_from_reader(a), [H.SubstrRegexDef.read_from_reader(x) for x in ss])
+                                            for a, ss in spec])
+    assert cfg.state_widths == [2, 2]
+    ocfg = O.OracleConfig([(O.OracleAllstr(a), [O.OracleSubstr(x) for x in ss]) for a, ss in spec], M)
+    assert ocfg.state_widths == [2, 2]
+    rng = random.Random(9)
+    strings = [bytes(rng.choice(b"aaaa bcdexyz@.") for _ in range(rng.randrange(0, M))) for _ in range(300)]
+    strings += [b"x" * 5 + s + b"a" * rng.randrange(0, 40) for s in SNIPPETS[:4]]
+    data, offs = _pack(strings)
+    g, gres = cfg.match_batch_host(data, offs, check=False, fill=0xCD, max_records=8, compact_pitch=16)
+    o, ores = ocfg.match_batch(data, offs, max_records=8, compact_pitch=16)
+    assert gres.code == ores.code
+    assert H.compare_outputs(g, o) == []
+    assert int(g.states[0 if order == "wide_first" else 1].max()) > 255
+
+
 def test_multiplicity_invariant_full_size_property():
     """Size-independent property at a larger N (oracle too slow to be the checker): sum(mult) = N*M, row 0 = padded
     rows, accepted fraction as planted, masked bytes equal the planted names."""
