@@ -187,6 +187,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     { const char* dbg = getenv("B2R_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
+    { const char* f = getenv("B2R_SPREAD_FILL"); p.spread_fill = (f && f[0] == '0') ? 0u : 1u; }   // testing hook
     { const char* f = getenv("B2R_FUSE"); p.fuse = (f && f[0] == '0') ? 0u : 1u; }   // testing hook: B2R_FUSE=0 runs emit_kernel as its own launch
     p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;

@@ -302,6 +302,11 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         // fused emit stage, fill: the tile's rows of every sparse column are contiguous.  Zero them with TMA bulk stores from
         // the shared zero buffer, one per lane, now; they complete in the background while the tile is walked (ordinary
         // stores would queue in the LSU in front of the other warps' table lookups).
+        // Each lane owns ops lane, lane+32, ... (numbered region by region).  Its first two are not issued here but spread
+        // over the chunk loop (op j at chunk j * n_chunks / n_ops): a burst of ~30 ops per warp backs up the bulk-copy queue
+        // (the issuing warps stall) and bunches the HBM writes in front of the other warps' input loads.
+        uint8_t *dz_ptr0 = nullptr, *dz_ptr1 = nullptr;
+        uint32_t dz_bytes0 = 0u, dz_bytes1 = 0u, dz_chunk0 = NO_POS, dz_chunk1 = NO_POS;
         if (p.fuse && !(p.debug & 1)) {
             const uint64_t cbytes = (uint64_t)rows_here * rp, bbytes = (uint64_t)rows_here * p.bitmap_pitch;
             uint8_t* reg_ptr[3 * D + 2];
@@ -314,7 +319,13 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
             reg_ptr[3 * D] = p.masked_chars ? p.masked_chars + tile_base * rp : nullptr; reg_bytes[3 * D] = cbytes;
             reg_ptr[3 * D + 1] = p.masked_substr_ids ? p.masked_substr_ids + tile_base * rp : nullptr; reg_bytes[3 * D + 1] = cbytes;
-            uint32_t first = 0;                                         // ops are numbered region by region; lane takes ops lane, lane+32, ...
+            uint32_t total_ops = 0;
+#pragma unroll
+            for (int r = 0; r < 3 * D + 2; r++)
+                if (reg_ptr[r]) total_ops += ((uint32_t)(reg_bytes[r] & ~15ull) + WALK_ZERO_BYTES - 1) / WALK_ZERO_BYTES;
+            const bool spread = p.spread_fill && n_chunks > 1;
+            const uint32_t sched_den = total_ops > n_chunks ? total_ops : n_chunks;
+            uint32_t first = 0;
 #pragma unroll
             for (int r = 0; r < 3 * D + 2; r++) {
                 if (!reg_ptr[r]) continue;
@@ -323,12 +334,18 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 for (uint32_t op = (lane + 32u - (first & 31u)) & 31u; op < n_ops; op += 32) {
                     const uint32_t o = op * WALK_ZERO_BYTES;
                     const uint32_t nb = bulk_bytes - o < WALK_ZERO_BYTES ? bulk_bytes - o : WALK_ZERO_BYTES;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reg_ptr[r] + o), "r"(zero_s), "r"(nb) : "memory");
+                    const uint32_t j = first + op;                      // j % 32 == lane
+                    if (spread && j < 64) {
+                        const uint32_t at = j * n_chunks / sched_den;
+                        if (j < 32) { dz_ptr0 = reg_ptr[r] + o; dz_bytes0 = nb; dz_chunk0 = at; }
+                        else { dz_ptr1 = reg_ptr[r] + o; dz_bytes1 = nb; dz_chunk1 = at; }
+                    } else {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reg_ptr[r] + o), "r"(zero_s), "r"(nb) : "memory");
+                    }
                 }
                 for (uint64_t o = bulk_bytes + (uint64_t)lane * 4; o < reg_bytes[r]; o += 128) *reinterpret_cast<uint32_t*>(reg_ptr[r] + o) = 0u;
                 first += n_ops;
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
 
         uint32_t fm = 0, fw0 = 0, fw1 = 0;                              // granule flags: current group of 32 granules, words 0 and 1
@@ -338,6 +355,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             const uint32_t cbase = chunk * DCH;
             if (chunk + 1 < n_chunks) { stage(chunk + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
             __syncwarp();
+            if (dz_chunk0 == chunk)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dz_ptr0), "r"(zero_s), "r"(dz_bytes0) : "memory");
+            if (dz_chunk1 == chunk)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dz_ptr1), "r"(zero_s), "r"(dz_bytes1) : "memory");
 
             const uint32_t my_in = in_s + (chunk & 1) * (32 * PITCH) + lane * PITCH;
 #pragma unroll 1
@@ -484,6 +505,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         }
         // ---- fused emit stage: the tile's states are in L1/L2, its flags and final states in registers --------------------
         if (p.fuse) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my zero-fill stores have completed ...
             __syncwarp();                                                 // ... and so have those of the other lanes
             uint32_t fin[D];

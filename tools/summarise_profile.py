@@ -59,3 +59,32 @@ json.dump(traffic, open(os.path.join(OUT, f"{tag}_walk_kernel_traffic.json"), "w
 print(open(os.path.join(OUT, f"{tag}_launches_summary.tsv")).read())
 print(open(os.path.join(OUT, f"{tag}_walk_kernel_full.txt")).read())
 print(traffic)
+
+# ---- where the warps wait: stall samples per SASS instruction (source page) -----------------------------------------
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sr = list(csv.reader(io.StringIO(src)))
+hi = next(i for i, r in enumerate(sr) if r and r[0] == "Address")
+sh, sd = sr[hi], sr[hi + 1:]
+six = {k: i for i, k in enumerate(sh)}
+def fnum(r, k):
+    try:
+        return float(r[six[k]])
+    except (ValueError, IndexError, KeyError):
+        return 0.0
+reasons = [k for k in sh if k.startswith("stall_") and "Not Issued" not in k]
+total = sum(fnum(r, "# Samples") for r in sd) or 1.0
+with open(os.path.join(OUT, f"{tag}_walk_kernel_stalls.tsv"), "w") as f:
+    f.write("# warp-state samples of the full capture by reason, then the 40 SASS instructions holding the most samples\n")
+    f.write("# (index = position in the kernel's SASS; a stall is charged to the instruction that could not issue, i.e. the consumer)\n")
+    for k in sorted(reasons, key=lambda k: -sum(fnum(r, k) for r in sd)):
+        v = sum(fnum(r, k) for r in sd)
+        if v / total >= 0.005:
+            f.write(f"{k}\t{v:.0f}\t{100 * v / total:.1f}%\n")
+    f.write("#\n# index\tsamples\tshare\texecuted\ttop reasons\tinstruction\n")
+    top = sorted(range(len(sd)), key=lambda i: -fnum(sd[i], "# Samples"))[:40]
+    for i in sorted(top):
+        r = sd[i]
+        best = sorted(((fnum(r, k), k[6:]) for k in reasons), reverse=True)[:2]
+        f.write(f"{i}\t{fnum(r, '# Samples'):.0f}\t{100 * fnum(r, '# Samples') / total:.1f}%\t{fnum(r, 'Instructions Executed'):.0f}\t"
+                + ", ".join(f"{n} {v:.0f}" for v, n in best if v) + f"\t{' '.join(r[six['Source']].split())}\n")
+print(open(os.path.join(OUT, f"{tag}_walk_kernel_stalls.tsv")).read())
