@@ -276,7 +276,8 @@ def main():
             alloc, keep = pinned_allocator(torch)
             h_in = alloc(in_bytes)
             h_in[:] = d_bytes.cpu().numpy()
-            h_offs = np.arange(n + 1, dtype=np.uint64) * L
+            h_offs = alloc((n + 1) * 8).view(np.uint64)
+            h_offs[:] = np.arange(n + 1, dtype=np.uint64) * L
             hout = HostOutputs(n, M, cfg.state_widths, cfg.table_num_rows, cfg.endpoint_num_rows, max_records=2, compact_pitch=8, allocator=alloc)
             cfg.match_batch_host(h_in, h_offs, out=hout)                        # warm-up (device staging allocation)
         except Exception as exc:  # pragma: no cover

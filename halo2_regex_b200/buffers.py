@@ -48,6 +48,15 @@ class HostOutputs:
                 a[:] = fill
             return a
 
+        def zeros(shape, dtype):
+            # every buffer comes from the allocator: one pageable destination makes its D2H copy synchronous
+            if not allocator:
+                return np.zeros(shape, dtype=dtype)
+            count = int(np.prod(shape))
+            a = allocator(count * np.dtype(dtype).itemsize)
+            a[:] = 0
+            return a.view(dtype).reshape(shape)
+
         self.states, self.substr_ids, self.start_enable, self.end_enable, self.mult, self.endpoint_mult = [], [], [], [], [], []
         for d in range(self.n_defs):
             w = state_widths[d]
@@ -55,13 +64,13 @@ class HostOutputs:
             self.substr_ids.append(col(n * rp).reshape(n, rp) if "substr_ids" in self.want else None)
             self.start_enable.append(col(n * bp).reshape(n, bp) if "start_enable" in self.want else None)
             self.end_enable.append(col(n * bp).reshape(n, bp) if "end_enable" in self.want else None)
-            self.mult.append(np.zeros(table_rows[d], dtype=np.uint64) if "mult" in self.want else None)
-            self.endpoint_mult.append(np.zeros(2 * endpoint_rows[d], dtype=np.uint64) if "endpoint_mult" in self.want else None)
+            self.mult.append(zeros(table_rows[d], np.uint64) if "mult" in self.want else None)
+            self.endpoint_mult.append(zeros(2 * endpoint_rows[d], np.uint64) if "endpoint_mult" in self.want else None)
         self.masked_chars = col(n * rp).reshape(n, rp) if "masked_chars" in self.want else None
         self.masked_substr_ids = col(n * rp).reshape(n, rp) if "masked_substr_ids" in self.want else None
-        self.status = np.zeros(n, dtype=_abi.STATUS_DTYPE) if "status" in self.want else None
-        self.records = np.zeros((n, self.max_records), dtype=_abi.RECORD_DTYPE) if "records" in self.want else None
-        self.compact_bytes = np.zeros((n, self.compact_pitch), dtype=np.uint8) if "compact_bytes" in self.want else None
+        self.status = zeros(n, _abi.STATUS_DTYPE) if "status" in self.want else None
+        self.records = zeros((n, self.max_records), _abi.RECORD_DTYPE) if "records" in self.want else None
+        self.compact_bytes = zeros((n, self.compact_pitch), np.uint8) if "compact_bytes" in self.want else None
 
     @staticmethod
     def _p(a):
