@@ -697,6 +697,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     for (uint32_t d = 0; d < c->n_defs; d++) {
         lp.def[d].byte_class = c->dev[d].byte_class; lp.def[d].trans = c->dev[d].trans;
         lp.def[d].num_states = c->packed[d].num_states; lp.def[d].first_state = c->packed[d].first_state;
+        lp.def[d].num_classes = c->packed[d].num_classes;
         lp.def[d].maps = (uint16_t*)(ws + off_maps[d]); lp.def[d].entry = (uint16_t*)(ws + off_entry[d]);
     }
     if ((rc = launch_long_prepare(lp, st, &c->last_launches))) return rc;

@@ -46,7 +46,7 @@ __global__ void diagnose_kernel(const __grid_constant__ WalkParams p, uint64_t j
 }
 
 // ---- launch planning ---------------------------------------------------------------------------------------------------
-static int device_limits(int* n_sm, int* max_smem) {
+int device_limits(int* n_sm, int* max_smem) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return B2R_ERR_CUDA; }
     cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, dev);

@@ -112,6 +112,7 @@ struct LaunchInfo {
 
 // host-callable launchers (kernels.cu / walk_inst.cu)
 // chooses table_mode / hist_mode for this device (force_* >= 0: preferred placement, testing hook); 0 or an error
+int device_limits(int* n_sm, int* max_smem);   // SM count and opt-in shared memory per block of the current device
 int plan_walk(WalkParams& p, bool wide_states, int force_table_mode, int force_hist_mode);
 int launch_walk(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);
 int launch_emit(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);

@@ -1,6 +1,7 @@
 // Launchers of the long-string path (long.cuh).
 #include "long.cuh"
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -41,13 +42,58 @@ __device__ __forceinline__ void long_chunk_range(const LongParams& p, uint32_t k
     mid = a + LONG_HEAD < b ? a + LONG_HEAD : b;
 }
 
+// ---- the same walks against tables staged in shared memory -----------------------------------------------------------------
+// cls_s[byte] = class * (S+1) (u16), tr_s[class * (S+1) + s] = next state (u16; S = the sticky trap state, also the image of
+// every invalid transition): one dependent shared-memory lookup per byte, no branch, the bytes read as 16-byte vectors one
+// vector ahead.  Used when class * (S+1) fits 16 bits and the tables fit in shared memory (long_tables_bytes).
+__host__ __device__ inline size_t long_tables_bytes(uint32_t S, uint32_t C) { return 512 + (size_t)C * (S + 1) * 2; }
+
+__device__ __forceinline__ void long_tables_init(const LongParams& p, uint32_t d, uint16_t* cls_s, uint16_t* tr_s) {
+    const uint32_t S = p.def[d].num_states, S1 = S + 1, C = p.def[d].num_classes;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls_s[i] = (uint16_t)(p.def[d].byte_class[i] * S1);
+    for (uint32_t i = threadIdx.x; i < C * S1; i += blockDim.x) {
+        const uint32_t c = i / S1, st = i % S1;
+        uint32_t nx = S;
+        if (st < S) { const uint32_t e = p.def[d].trans[c * S + st]; nx = (e & ENT_INVALID) ? S : (e & ENT_NEXT_MASK); }
+        tr_s[i] = (uint16_t)nx;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t long_walk_s(const uint8_t* __restrict__ bytes, uint64_t a, uint64_t b, uint32_t s, const uint16_t* cls_s,
+                                                const uint16_t* tr_s) {
+    uint64_t i = a;
+    for (; i < b && ((uintptr_t)(bytes + i) & 15u); i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
+    if (i + 16 <= b) {
+        uint4 nxt = __ldg(reinterpret_cast<const uint4*>(bytes + i));
+        for (; i + 16 <= b; i += 16) {
+            const uint4 v = nxt;
+            if (i + 32 <= b) nxt = __ldg(reinterpret_cast<const uint4*>(bytes + i + 16));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t c0 = cls_s[w[q] & 255u], c1 = cls_s[(w[q] >> 8) & 255u], c2 = cls_s[(w[q] >> 16) & 255u], c3 = cls_s[w[q] >> 24];
+                s = tr_s[c0 + s]; s = tr_s[c1 + s]; s = tr_s[c2 + s]; s = tr_s[c3 + s];
+            }
+        }
+    }
+    for (; i < b; i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
+    return s;
+}
+
+template <bool SMEM>
 __global__ void __launch_bounds__(256) long_maps_head_kernel(const __grid_constant__ LongParams p, uint32_t d) {
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    uint16_t* cls_s = reinterpret_cast<uint16_t*>(long_smem);
+    uint16_t* tr_s = cls_s + 256;
+    if (SMEM) long_tables_init(p, d, cls_s, tr_s);
     const uint32_t S1 = p.def[d].num_states + 1;
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)p.n_chunks * S1) return;
-    uint64_t a, mid, b;
-    long_chunk_range(p, (uint32_t)(t / S1), a, mid, b);
-    p.def[d].maps[t] = (uint16_t)long_walk(p, d, (uint32_t)(t % S1), a, mid);
+    const uint64_t total = (uint64_t)p.n_chunks * S1;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t a, mid, b;
+        long_chunk_range(p, (uint32_t)(t / S1), a, mid, b);
+        p.def[d].maps[t] = (uint16_t)(SMEM ? long_walk_s(p.bytes, a, mid, (uint32_t)(t % S1), cls_s, tr_s) : long_walk(p, d, (uint32_t)(t % S1), a, mid));
+    }
 }
 
 // uniq[k][0..LONG_MAXU): the distinct images of chunk k (count in n_uniq[k]; LONG_MAXU+1 = more than that: wide chunk);
@@ -71,26 +117,38 @@ __global__ void __launch_bounds__(256) long_dedupe_kernel(const __grid_constant_
 }
 
 // narrow chunks: thread per (chunk, distinct image) walks the rest of the chunk; result overwrites uniq
+template <bool SMEM>
 __global__ void __launch_bounds__(256) long_maps_tail_kernel(const __grid_constant__ LongParams p, uint32_t d, uint16_t* uniq, const uint8_t* n_uniq) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)p.n_chunks * LONG_MAXU) return;
-    const uint32_t k = (uint32_t)(t / LONG_MAXU), j = (uint32_t)(t % LONG_MAXU);
-    if (j >= n_uniq[k] || n_uniq[k] > LONG_MAXU) return;
-    uint64_t a, mid, b;
-    long_chunk_range(p, k, a, mid, b);
-    uniq[t] = (uint16_t)long_walk(p, d, uniq[t], mid, b);
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    uint16_t* cls_s = reinterpret_cast<uint16_t*>(long_smem);
+    uint16_t* tr_s = cls_s + 256;
+    if (SMEM) long_tables_init(p, d, cls_s, tr_s);
+    const uint64_t total = (uint64_t)p.n_chunks * LONG_MAXU;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(t / LONG_MAXU), j = (uint32_t)(t % LONG_MAXU);
+        if (j >= n_uniq[k] || n_uniq[k] > LONG_MAXU) continue;
+        uint64_t a, mid, b;
+        long_chunk_range(p, k, a, mid, b);
+        uniq[t] = (uint16_t)(SMEM ? long_walk_s(p.bytes, mid, b, uniq[t], cls_s, tr_s) : long_walk(p, d, uniq[t], mid, b));
+    }
 }
 
 // thread per (chunk, state): narrow chunks gather the result of their image, wide chunks walk the rest themselves
+template <bool SMEM>
 __global__ void __launch_bounds__(256) long_maps_gather_kernel(const __grid_constant__ LongParams p, uint32_t d, const uint16_t* uniq, const uint8_t* n_uniq, const uint8_t* which) {
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    uint16_t* cls_s = reinterpret_cast<uint16_t*>(long_smem);
+    uint16_t* tr_s = cls_s + 256;
+    if (SMEM) long_tables_init(p, d, cls_s, tr_s);
     const uint32_t S1 = p.def[d].num_states + 1;
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)p.n_chunks * S1) return;
-    const uint32_t k = (uint32_t)(t / S1);
-    if (n_uniq[k] <= LONG_MAXU) { p.def[d].maps[t] = uniq[(size_t)k * LONG_MAXU + which[t]]; return; }
-    uint64_t a, mid, b;
-    long_chunk_range(p, k, a, mid, b);
-    p.def[d].maps[t] = (uint16_t)long_walk(p, d, p.def[d].maps[t], mid, b);
+    const uint64_t total = (uint64_t)p.n_chunks * S1;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(t / S1);
+        if (n_uniq[k] <= LONG_MAXU) { p.def[d].maps[t] = uniq[(size_t)k * LONG_MAXU + which[t]]; continue; }
+        uint64_t a, mid, b;
+        long_chunk_range(p, k, a, mid, b);
+        p.def[d].maps[t] = (uint16_t)(SMEM ? long_walk_s(p.bytes, mid, b, p.def[d].maps[t], cls_s, tr_s) : long_walk(p, d, p.def[d].maps[t], mid, b));
+    }
 }
 
 // level l+1 map i = composition of its (up to 64) children at level l; thread per (node, state)
@@ -233,13 +291,31 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
     for (uint32_t d = 0; d < lp.n_defs; d++) {
         const uint32_t S1 = lp.def[d].num_states + 1;
         const uint64_t threads = (uint64_t)lp.n_chunks * S1;
-        long_maps_head_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d);
+        // tables in shared memory when they fit (and class * (S+1) fits the u16 of the class table)
+        int n_sm = 0, max_smem = 0;
+        { const int rc = device_limits(&n_sm, &max_smem); if (rc) return rc; }
+        const size_t tb = long_tables_bytes(lp.def[d].num_states, lp.def[d].num_classes);
+        const bool smem_ok = (uint64_t)lp.def[d].num_classes * S1 <= 65535u && tb <= (size_t)max_smem;
+        const size_t smem = smem_ok ? tb : 0;
+        const unsigned per_sm = smem_ok ? (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / (tb + 1024))) : 8u;
+        auto grid_for = [&](uint64_t work) { const uint64_t need = (work + 255) / 256, cap = (uint64_t)n_sm * per_sm; return (unsigned)std::max<uint64_t>(1, std::min(need, cap)); };
+        if (smem > 48 * 1024) {
+            if (cudaFuncSetAttribute(long_maps_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(long_maps_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(long_maps_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(long_maps_*_kernel)"); return B2R_ERR_CUDA;
+            }
+        }
+        if (smem_ok) long_maps_head_kernel<true><<<grid_for(threads), 256, smem, st>>>(lp, d);
+        else long_maps_head_kernel<false><<<grid_for(threads), 256, 0, st>>>(lp, d);
         LAUNCH_CHECK("long_maps_head_kernel"); (*launches)++;
         long_dedupe_kernel<<<(lp.n_chunks + 255) / 256, 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
         LAUNCH_CHECK("long_dedupe_kernel"); (*launches)++;
-        long_maps_tail_kernel<<<(unsigned)(((uint64_t)lp.n_chunks * LONG_MAXU + 255) / 256), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq);
+        if (smem_ok) long_maps_tail_kernel<true><<<grid_for((uint64_t)lp.n_chunks * LONG_MAXU), 256, smem, st>>>(lp, d, lp.uniq, lp.n_uniq);
+        else long_maps_tail_kernel<false><<<grid_for((uint64_t)lp.n_chunks * LONG_MAXU), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq);
         LAUNCH_CHECK("long_maps_tail_kernel"); (*launches)++;
-        long_maps_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
+        if (smem_ok) long_maps_gather_kernel<true><<<grid_for(threads), 256, smem, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
+        else long_maps_gather_kernel<false><<<grid_for(threads), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
         LAUNCH_CHECK("long_maps_gather_kernel"); (*launches)++;
         // up the tree
         std::vector<uint32_t> n_level{lp.n_chunks};

@@ -31,7 +31,7 @@ struct LongParams {
     struct {
         const uint8_t* byte_class;
         const uint32_t* trans;           // [C][S] packed entries (defs.hpp)
-        uint32_t num_states, first_state;
+        uint32_t num_states, first_state, num_classes;
         uint16_t* maps;                  // all levels back to back: level 0 [n_chunks][S+1], level 1 [ceil(n/64)][S+1], ...
         uint16_t* entry;                 // all levels back to back: entry state of every node
     } def[B2R_MAX_DEFS];
