@@ -172,6 +172,48 @@ __global__ void __launch_bounds__(256) long_propagate_kernel(const uint16_t* chi
     for (uint32_t c = c0; c < c1; c++) { child_entry[c] = (uint16_t)s; s = child_maps[(size_t)c * S1 + s]; }
 }
 
+// The same tree with one CTA per parent node: a Hillis-Steele scan (composition is associative, not commutative: earlier
+// children are applied first) over its <= 64 children in shared memory.  The child maps are replaced IN PLACE by their
+// exclusive prefixes E_c = f_{c-1} o ... o f_0 (E_0 = identity); the parent gets the composition of all of them.
+__global__ void __launch_bounds__(256) long_scan_kernel(uint16_t* child_maps, uint16_t* parent_maps, uint32_t n_child, uint32_t S1) {
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    uint16_t* A = reinterpret_cast<uint16_t*>(long_smem);
+    uint16_t* B = A + (size_t)LONG_FANOUT * S1;
+    const uint32_t c0 = blockIdx.x * LONG_FANOUT;
+    const uint32_t nc = n_child - c0 < LONG_FANOUT ? n_child - c0 : LONG_FANOUT;
+    const uint32_t tot = nc * S1;
+    uint16_t* mine = child_maps + (size_t)c0 * S1;
+    for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) A[i] = mine[i];
+    __syncthreads();
+    for (uint32_t o = 1; o < nc; o <<= 1) {
+        for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) {
+            const uint32_t c = i / S1, s = i - c * S1;
+            B[i] = c >= o ? A[c * S1 + A[(c - o) * S1 + s]] : A[i];
+        }
+        __syncthreads();
+        uint16_t* t = A; A = B; B = t;
+    }
+    for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) {
+        const uint32_t c = i / S1, s = i - c * S1;
+        mine[i] = c == 0 ? (uint16_t)s : A[(c - 1) * S1 + s];
+    }
+    for (uint32_t s = threadIdx.x; s < S1; s += blockDim.x) parent_maps[(size_t)blockIdx.x * S1 + s] = A[(nc - 1) * S1 + s];
+}
+
+// entry state of every chunk: first_state pushed down through the exclusive prefixes of its ancestors; thread per chunk
+struct LongLevels { uint32_t n; uint32_t off[12]; };   // off[l]: first node of level l in `maps` (level 0 = chunks)
+__global__ void __launch_bounds__(256) long_resolve_kernel(const uint16_t* maps, uint16_t* entry0, LongLevels lv, uint32_t n_chunks, uint32_t S1, uint32_t first) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    uint32_t s = first;
+    for (int l = (int)lv.n - 2; l >= 0; l--) {
+        uint32_t node = c;
+        for (int k = 0; k < l; k++) node /= LONG_FANOUT;
+        s = maps[((size_t)lv.off[l] + node) * S1 + s];
+    }
+    entry0[c] = (uint16_t)s;
+}
+
 // bit c of word w: chunk 32w + c has a flagged granule
 __global__ void __launch_bounds__(256) long_summary_kernel(const uint32_t* fmask, uint32_t fm_words, uint32_t n_chunks, uint32_t* summary) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +365,23 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
         while (n_level.back() > 1) {
             off_level.push_back(off_level.back() + n_level.back());
             n_level.push_back((n_level.back() + LONG_FANOUT - 1) / LONG_FANOUT);
+        }
+        const size_t scan_smem = 2 * (size_t)LONG_FANOUT * S1 * sizeof(uint16_t);
+        if (scan_smem <= (size_t)max_smem && n_level.size() <= 12) {
+            // one CTA per parent node: scan in shared memory, exclusive prefixes left in place of the child maps
+            if (scan_smem > 48 * 1024 && cudaFuncSetAttribute(long_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem) != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(long_scan_kernel)"); return B2R_ERR_CUDA;
+            }
+            for (size_t l = 0; l + 1 < n_level.size(); l++) {
+                long_scan_kernel<<<n_level[l + 1], 256, scan_smem, st>>>(lp.def[d].maps + off_level[l] * S1, lp.def[d].maps + off_level[l + 1] * S1, n_level[l], S1);
+                LAUNCH_CHECK("long_scan_kernel"); (*launches)++;
+            }
+            LongLevels lv;
+            lv.n = (uint32_t)n_level.size();
+            for (size_t l = 0; l < n_level.size(); l++) lv.off[l] = (uint32_t)off_level[l];
+            long_resolve_kernel<<<(lp.n_chunks + 255) / 256, 256, 0, st>>>(lp.def[d].maps, lp.def[d].entry, lv, lp.n_chunks, S1, lp.def[d].first_state);
+            LAUNCH_CHECK("long_resolve_kernel"); (*launches)++;
+            continue;
         }
         for (size_t l = 0; l + 1 < n_level.size(); l++) {
             const uint32_t nc = n_level[l], np = n_level[l + 1];
