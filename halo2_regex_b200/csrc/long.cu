@@ -64,19 +64,26 @@ __device__ __forceinline__ uint32_t long_walk_s(const uint8_t* __restrict__ byte
                                                 const uint16_t* tr_s) {
     uint64_t i = a;
     for (; i < b && ((uintptr_t)(bytes + i) & 15u); i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
-    if (i + 16 <= b) {
-        uint4 nxt = __ldg(reinterpret_cast<const uint4*>(bytes + i));
-        for (; i + 16 <= b; i += 16) {
-            const uint4 v = nxt;
-            if (i + 32 <= b) nxt = __ldg(reinterpret_cast<const uint4*>(bytes + i + 16));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    auto step16 = [&](const uint4& v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t c0 = cls_s[w[q] & 255u], c1 = cls_s[(w[q] >> 8) & 255u], c2 = cls_s[(w[q] >> 16) & 255u], c3 = cls_s[w[q] >> 24];
-                s = tr_s[c0 + s]; s = tr_s[c1 + s]; s = tr_s[c2 + s]; s = tr_s[c3 + s];
-            }
+        for (int q = 0; q < 4; q++) {
+            const uint32_t c0 = cls_s[w[q] & 255u], c1 = cls_s[(w[q] >> 8) & 255u], c2 = cls_s[(w[q] >> 16) & 255u], c3 = cls_s[w[q] >> 24];
+            s = tr_s[c0 + s]; s = tr_s[c1 + s]; s = tr_s[c2 + s]; s = tr_s[c3 + s];
+        }
+    };
+    // 64 bytes per round, the next round's four vectors in flight while this one is walked (one vector ahead does not cover
+    // the DRAM latency: a vector is ~16 dependent shared-memory lookups)
+    if (i + 64 <= b) {
+        const uint4* q = reinterpret_cast<const uint4*>(bytes + i);
+        uint4 n0 = __ldg(q), n1 = __ldg(q + 1), n2 = __ldg(q + 2), n3 = __ldg(q + 3);
+        for (; i + 64 <= b; i += 64) {
+            const uint4 v0 = n0, v1 = n1, v2 = n2, v3 = n3;
+            if (i + 128 <= b) { q = reinterpret_cast<const uint4*>(bytes + i + 64); n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2); n3 = __ldg(q + 3); }
+            step16(v0); step16(v1); step16(v2); step16(v3);
         }
     }
+    for (; i + 16 <= b; i += 16) step16(__ldg(reinterpret_cast<const uint4*>(bytes + i)));
     for (; i < b; i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
     return s;
 }
