@@ -75,6 +75,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---- shared-memory layout, computed identically by the launcher and the kernel ---------------------------------------------
 // bytes between consecutive table entries; class-table entries are 4 bytes (128 when replicated)
+// in-row XOR swizzle of class row k of a single-copy table (row_bytes = padded_states * stride, a power of two): words
+__host__ __device__ inline uint32_t walk_swizzle(uint32_t k, uint32_t row_bytes) { return (k << 2) & (row_bytes - 1u) & 0x7Cu; }
 __host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : table_mode == TABLE_PLAIN16 ? 2u : 4u; }
 __host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : 4u; }
 __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
@@ -161,15 +163,19 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             for (uint32_t i = threadIdx.x; i < (n << csh); i += blockDim.x) {
                 const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u);
                 const uint32_t e = __ldg(p.def[d].hot + idx);
-                if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + idx * 2), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
-                else sts32(t0 + idx * stride + l * 4, e | ((e >> 16) * stride));
+                // single-copy tables: row k is XOR-swizzled by its class (walk_swizzle) — lanes in the same state with
+                // different classes would otherwise all hit one bank (the row size is a power of two)
+                const uint32_t swz = TM == (int)TABLE_REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
+                if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
+                else sts32(t0 + ((idx * stride) ^ swz) + l * 4, e | ((e >> 16) * stride));
             }
         }
         for (uint32_t i = threadIdx.x; i < (256u << csh); i += blockDim.x) {
             const uint32_t c = i >> csh, l = i & ((1u << csh) - 1u);
             uint32_t v;
             if (D == 1) {
-                v = base_s + lay.tab[0] + (uint32_t)__ldg(p.def[0].byte_class + c) * p.def[0].padded_states * stride + l * 4;
+                const uint32_t k = __ldg(p.def[0].byte_class + c), rb = p.def[0].padded_states * stride;
+                v = base_s + lay.tab[0] + k * rb + l * 4 + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rb));
             } else {
                 v = 0;
 #pragma unroll
@@ -220,9 +226,15 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     // one position of def d: `cur` is the entry that led to the current state, c the byte.  Returns the next entry.
     auto lookup = [&](int d, uint32_t cur, uint32_t c, uint32_t cent) -> uint32_t {
         if (SMEM_TAB) {
-            const uint32_t row = (D == 1) ? cent : tabl[d] + ((cent >> (8 * d)) & 0xFFu) * rowb[d];
-            if (E16) { uint32_t e; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((cur & 0xFFFEu) | row)); return e; }
-            return lds32((cur & 0xFFFCu) | row);
+            uint32_t row;
+            if (D == 1) row = cent;
+            else {
+                const uint32_t k = (cent >> (8 * d)) & 0xFFu;
+                row = tabl[d] + k * rowb[d] + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rowb[d]));
+            }
+            // XOR, not OR: the low bits of `row` of a single-copy table carry the class swizzle (they are zero otherwise)
+            if (E16) { uint32_t e; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((cur & 0xFFFEu) ^ row)); return e; }
+            return lds32((cur & 0xFFFCu) ^ row);
         } else {
             const uint32_t k = __ldg(p.def[d].byte_class + c);
             return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> NSH));
