@@ -60,20 +60,25 @@ __device__ __forceinline__ void long_tables_init(const LongParams& p, uint32_t d
     __syncthreads();
 }
 
-__device__ __forceinline__ uint32_t long_walk_s(const uint8_t* __restrict__ bytes, uint64_t a, uint64_t b, uint32_t s, const uint16_t* cls_s,
-                                                const uint16_t* tr_s) {
+// N independent walks over the same bytes (the distinct images of one chunk): one class lookup per byte serves all of them
+template <int N>
+__device__ __forceinline__ void long_walk_n(const uint8_t* __restrict__ bytes, uint64_t a, uint64_t b, uint32_t (&s)[N], const uint16_t* cls_s,
+                                            const uint16_t* tr_s) {
+    auto step = [&](uint32_t c) {
+#pragma unroll
+        for (int n = 0; n < N; n++) s[n] = tr_s[c + s[n]];
+    };
     uint64_t i = a;
-    for (; i < b && ((uintptr_t)(bytes + i) & 15u); i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
+    for (; i < b && ((uintptr_t)(bytes + i) & 15u); i++) step(cls_s[__ldg(bytes + i)]);
     auto step16 = [&](const uint4& v) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t c0 = cls_s[w[q] & 255u], c1 = cls_s[(w[q] >> 8) & 255u], c2 = cls_s[(w[q] >> 16) & 255u], c3 = cls_s[w[q] >> 24];
-            s = tr_s[c0 + s]; s = tr_s[c1 + s]; s = tr_s[c2 + s]; s = tr_s[c3 + s];
+            step(c0); step(c1); step(c2); step(c3);
         }
     };
-    // 64 bytes per round, the next round's four vectors in flight while this one is walked (one vector ahead does not cover
-    // the DRAM latency: a vector is ~16 dependent shared-memory lookups)
+    // 64 bytes per round, the next round's four vectors in flight while this one is walked
     if (i + 64 <= b) {
         const uint4* q = reinterpret_cast<const uint4*>(bytes + i);
         uint4 n0 = __ldg(q), n1 = __ldg(q + 1), n2 = __ldg(q + 2), n3 = __ldg(q + 3);
@@ -84,8 +89,14 @@ __device__ __forceinline__ uint32_t long_walk_s(const uint8_t* __restrict__ byte
         }
     }
     for (; i + 16 <= b; i += 16) step16(__ldg(reinterpret_cast<const uint4*>(bytes + i)));
-    for (; i < b; i++) s = tr_s[cls_s[__ldg(bytes + i)] + s];
-    return s;
+    for (; i < b; i++) step(cls_s[__ldg(bytes + i)]);
+}
+
+__device__ __forceinline__ uint32_t long_walk_s(const uint8_t* __restrict__ bytes, uint64_t a, uint64_t b, uint32_t s0, const uint16_t* cls_s,
+                                                const uint16_t* tr_s) {
+    uint32_t s[1] = {s0};
+    long_walk_n<1>(bytes, a, b, s, cls_s, tr_s);
+    return s[0];
 }
 
 template <bool SMEM>
@@ -130,13 +141,31 @@ __global__ void __launch_bounds__(256) long_maps_tail_kernel(const __grid_consta
     uint16_t* cls_s = reinterpret_cast<uint16_t*>(long_smem);
     uint16_t* tr_s = cls_s + 256;
     if (SMEM) long_tables_init(p, d, cls_s, tr_s);
+    if (SMEM) {
+        // thread per chunk: its (<= 4) distinct images walk together
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < p.n_chunks; k += gridDim.x * blockDim.x) {
+            const uint32_t n = n_uniq[k];
+            if (n > LONG_MAXU) continue;
+            uint64_t a, mid, b;
+            long_chunk_range(p, k, a, mid, b);
+            uint16_t* u = uniq + (size_t)k * LONG_MAXU;
+            if (n == 1) { uint32_t s[1] = {u[0]}; long_walk_n<1>(p.bytes, mid, b, s, cls_s, tr_s); u[0] = (uint16_t)s[0]; }
+            else if (n == 2) { uint32_t s[2] = {u[0], u[1]}; long_walk_n<2>(p.bytes, mid, b, s, cls_s, tr_s); u[0] = (uint16_t)s[0]; u[1] = (uint16_t)s[1]; }
+            else {
+                uint32_t s[4] = {u[0], u[1], u[2], n == 4 ? (uint32_t)u[3] : p.def[d].num_states};
+                long_walk_n<4>(p.bytes, mid, b, s, cls_s, tr_s);
+                for (uint32_t j = 0; j < n; j++) u[j] = (uint16_t)s[j];
+            }
+        }
+        return;
+    }
     const uint64_t total = (uint64_t)p.n_chunks * LONG_MAXU;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(t / LONG_MAXU), j = (uint32_t)(t % LONG_MAXU);
         if (j >= n_uniq[k] || n_uniq[k] > LONG_MAXU) continue;
         uint64_t a, mid, b;
         long_chunk_range(p, k, a, mid, b);
-        uniq[t] = (uint16_t)(SMEM ? long_walk_s(p.bytes, mid, b, uniq[t], cls_s, tr_s) : long_walk(p, d, uniq[t], mid, b));
+        uniq[t] = (uint16_t)long_walk(p, d, uniq[t], mid, b);
     }
 }
 
@@ -348,6 +377,8 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
         const size_t smem = smem_ok ? tb : 0;
         const unsigned per_sm = smem_ok ? (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / (tb + 1024))) : 8u;
         auto grid_for = [&](uint64_t work) { const uint64_t need = (work + 255) / 256, cap = (uint64_t)n_sm * per_sm; return (unsigned)std::max<uint64_t>(1, std::min(need, cap)); };
+        // thread per chunk: small CTAs so that the chunks spread over all SMs
+        auto grid_for_small = [&](uint64_t work) { const uint64_t need = (work + 63) / 64, cap = (uint64_t)n_sm * per_sm * 4; return (unsigned)std::max<uint64_t>(1, std::min(need, cap)); };
         if (smem > 48 * 1024) {
             if (cudaFuncSetAttribute(long_maps_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
                 cudaFuncSetAttribute(long_maps_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -360,7 +391,7 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
         LAUNCH_CHECK("long_maps_head_kernel"); (*launches)++;
         long_dedupe_kernel<<<(lp.n_chunks + 255) / 256, 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
         LAUNCH_CHECK("long_dedupe_kernel"); (*launches)++;
-        if (smem_ok) long_maps_tail_kernel<true><<<grid_for((uint64_t)lp.n_chunks * LONG_MAXU), 256, smem, st>>>(lp, d, lp.uniq, lp.n_uniq);
+        if (smem_ok) long_maps_tail_kernel<true><<<grid_for_small(lp.n_chunks), 64, smem, st>>>(lp, d, lp.uniq, lp.n_uniq);
         else long_maps_tail_kernel<false><<<grid_for((uint64_t)lp.n_chunks * LONG_MAXU), 256, 0, st>>>(lp, d, lp.uniq, lp.n_uniq);
         LAUNCH_CHECK("long_maps_tail_kernel"); (*launches)++;
         if (smem_ok) long_maps_gather_kernel<true><<<grid_for(threads), 256, smem, st>>>(lp, d, lp.uniq, lp.n_uniq, lp.which);
