@@ -220,3 +220,42 @@ def test_compiled_definitions_on_gpu(name):
     o, ores = ocfg.match_batch(data, offs, max_records=8, compact_pitch=16)
     assert (gres.code, gres.string_idx, gres.pos) == (ores.code, ores.string_idx, ores.pos)
     assert H.compare_outputs(g, o) == []
+
+
+def _random_regex(rng, depth=0):
+    """Random expression over {a, b, c} in the grammar regex.js:216-233 parses (no empty alternatives)."""
+    r = rng.random()
+    if depth >= 3 or r < 0.3:
+        return rng.choice("abc")
+    if r < 0.5:
+        return _random_regex(rng, depth + 1) + _random_regex(rng, depth + 1)
+    if r < 0.7:
+        return "(" + _random_regex(rng, depth + 1) + "|" + _random_regex(rng, depth + 1) + ")"
+    return "(" + _random_regex(rng, depth + 1) + ")" + rng.choice("*+?")
+
+
+def test_random_regexes_accept_what_a_backtracking_engine_accepts():
+    """Parser, Thompson construction, subset construction and Hopcroft together, against Python's `re` on all strings
+    over {a, b, c} up to length 5 (and some longer ones)."""
+    import itertools
+    import random
+    import re
+    rng = random.Random(2024)
+    short = ["".join(t) for n in range(6) for t in itertools.product("abc", repeat=n)]
+    for _ in range(60):
+        rx = _random_regex(rng)
+        graph = vrm.regex_to_dfa(rx)
+        ref = re.compile(rx)
+        texts = short + ["".join(rng.choice("abc") for _ in range(rng.randrange(6, 14))) for _ in range(50)]
+        for t in texts:
+            assert _accepts(graph, t) == (ref.fullmatch(t) is not None), (rx, t)
+        # minimal: no two states are equivalent (Moore refinement of the result does not merge anything)
+        cls = [1 if st["type"] == "accept" else 0 for st in graph]
+        while True:
+            sig = [(cls[i], tuple(sorted((ch, cls[to]) for key, to in st["edges"].items() for ch in json.loads(key)))) for i, st in enumerate(graph)]
+            ids = {}
+            new = [ids.setdefault(s, len(ids)) for s in sig]
+            if len(ids) == len(set(cls)):
+                break
+            cls = new
+        assert len(set(cls)) == len(graph), rx
