@@ -662,7 +662,6 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     cudaStream_t st = (cudaStream_t)cuda_stream;
     bool wide = false;
     for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
-    for (uint32_t d = 0; d < c->n_defs; d++)
     c->last_launches = 0;
     CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
     CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none
@@ -741,6 +740,60 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     if (rc) return rc;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], st));
     return B2R_OK;
+}
+
+// Host-pointer variant of the long-string path: the string goes up in one copy, the columns come back in one copy each.
+int b2r_match_long_host(b2r_config* c, const uint8_t* h_bytes, uint64_t len, const b2r_outputs* ho, b2r_batch_status* result) {
+    if (!c || !ho || (!h_bytes && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
+    const uint64_t M = len + 1;
+    int rc = check_outputs(c, ho, false, M);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
+    cudaStream_t st = c->host_stream;
+    if ((rc = c->ws_bytes.reserve(align_up(len + 16, 256)))) return rc;
+    const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
+    size_t need = 0;
+    auto slot = [&](size_t bytes) { size_t o = need; need += align_up(bytes, 256); return o; };
+    struct Copy { size_t off; void* host; size_t bytes; };
+    std::vector<Copy> copies;
+    std::vector<size_t> offs;
+    b2r_outputs dout = *ho;
+    auto want = [&](void* host, size_t bytes) -> size_t {
+        if (!host) { offs.push_back(0); return 0; }
+        const size_t o = slot(bytes);
+        copies.push_back({o, host, bytes});
+        offs.push_back(o);
+        return o;
+    };
+    // first pass: sizes; second pass (after the reserve): device pointers
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        want(ho->states[d], rp * c->packed[d].state_width); want(ho->substr_ids[d], rp); want(ho->start_enable[d], bp); want(ho->end_enable[d], bp);
+        want(ho->mult[d], c->packed[d].rows.size() * 8); want(ho->endpoint_mult[d], c->packed[d].erows.size() * 16);
+    }
+    want(ho->masked_chars, rp); want(ho->masked_substr_ids, rp); want(ho->status, sizeof(b2r_string_status));
+    want(ho->records, (size_t)ho->max_records * sizeof(b2r_substr_record)); want(ho->compact_bytes, (size_t)ho->compact_pitch);
+    if ((rc = c->ws_cols.reserve(need + 256))) return rc;
+    unsigned char* cb = (unsigned char*)c->ws_cols.p;
+    size_t k = 0;
+    auto dev = [&](void* host) -> void* { const size_t o = offs[k++]; return host ? cb + o : nullptr; };
+    for (uint32_t d = 0; d < c->n_defs; d++) {
+        dout.states[d] = dev(ho->states[d]); dout.substr_ids[d] = (uint8_t*)dev(ho->substr_ids[d]);
+        dout.start_enable[d] = (uint8_t*)dev(ho->start_enable[d]); dout.end_enable[d] = (uint8_t*)dev(ho->end_enable[d]);
+        dout.mult[d] = (uint64_t*)dev(ho->mult[d]); dout.endpoint_mult[d] = (uint64_t*)dev(ho->endpoint_mult[d]);
+        if (ho->flags & B2R_OUT_ACCUMULATE_MULT) {
+            if (ho->mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.mult[d], ho->mult[d], c->packed[d].rows.size() * 8, cudaMemcpyHostToDevice, st));
+            if (ho->endpoint_mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.endpoint_mult[d], ho->endpoint_mult[d], c->packed[d].erows.size() * 16, cudaMemcpyHostToDevice, st));
+        }
+    }
+    dout.masked_chars = (uint8_t*)dev(ho->masked_chars); dout.masked_substr_ids = (uint8_t*)dev(ho->masked_substr_ids);
+    dout.status = (b2r_string_status*)dev(ho->status); dout.records = (b2r_substr_record*)dev(ho->records);
+    dout.compact_bytes = (uint8_t*)dev(ho->compact_bytes);
+    if (len) CUDA_TRY(cudaMemcpyAsync(c->ws_bytes.p, h_bytes, len, cudaMemcpyHostToDevice, st));
+    if ((rc = b2r_match_long(c, (const uint8_t*)c->ws_bytes.p, len, &dout, st))) return rc;
+    for (const Copy& cp : copies) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
+    return b2r_batch_result(c, st, result);
 }
 
 uint32_t b2r_last_launch_count(const b2r_config* c) { return c ? c->last_launches : 0; }

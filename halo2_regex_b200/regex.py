@@ -253,6 +253,19 @@ class RegexVerifyConfig:
         _raise(rc)
         return out
 
+    def match_long_host(self, data, out=None, check=True, **kw):
+        """b2r_match_long_host: ONE string (host bytes) through the chunked long-string path, max_chars_size = len + 1;
+        host buffers out (`out`: HostOutputs(1, len + 1, ...), allocated here if not given)."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+        if out is None:
+            out = HostOutputs(1, len(data) + 1, self.state_widths, self.table_num_rows, self.endpoint_num_rows, **kw)
+        st = out.struct(0)
+        res = _abi.BatchStatus()
+        rc = lib.b2r_match_long_host(self._h, data.ctypes.data, len(data), C.byref(st), C.byref(res))
+        if check:
+            _raise(rc, res)
+        return out, res
+
     def batch_result(self, stream=None, check=True):
         import torch
         if stream is None:

@@ -225,6 +225,11 @@ int b2r_match_substrs(b2r_config* cfg, const uint8_t* characters, uint64_t len, 
 int b2r_match_long(b2r_config* cfg, const uint8_t* d_bytes, uint64_t len, const b2r_outputs* d_out,
                    void* cuda_stream);
 
+/* The same with host pointers (the shape a shim around match_substrs, src/lib.rs:311-315, has for one very long input):
+ * the string is copied up, the M = len+1 rows of every requested column are copied back; row_pitch >= M. */
+int b2r_match_long_host(b2r_config* cfg, const uint8_t* h_bytes, uint64_t len, const b2r_outputs* h_out,
+                        b2r_batch_status* result);
+
 /* kernel launches enqueued by the last b2r_match_* call on this handle (for benchmark accounting) */
 uint32_t b2r_last_launch_count(const b2r_config*);
 /* name + device time (ms, CUDA events on the launching stream) of the dominant kernel of the last call;

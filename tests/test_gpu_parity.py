@@ -366,6 +366,27 @@ def test_long_string_path(set_name, length):
     assert H.compare_outputs(out.to_host(), o) == []
 
 
+@pytest.mark.parametrize("set_name,length", [("regex1", 0), ("regex1", 5000), ("test1", 70001), ("regex3", 1024)])
+def test_long_string_host_entry_point(set_name, length):
+    """b2r_match_long_host: host bytes in, host columns out, same answer as the oracle with max_chars_size = len + 1."""
+    rng = random.Random(length + 5)
+    body = bytearray(rng.choice(b"abc xyz.@\r\n") for _ in range(length))
+    for snip in SNIPPETS[:5]:
+        if length > 200:
+            at = rng.randrange(0, length - len(snip))
+            body[at:at + len(snip)] = snip
+    s = bytes(body)
+    M = length + 1
+    cfg = product_config(set_name, 64)
+    ocfg = oracle_config(set_name, M)
+    g, gres = cfg.match_long_host(s, check=False, max_records=8, compact_pitch=64, fill=0xCD)
+    data, offs = _pack([s])
+    o, ores = ocfg.match_batch(data, offs, max_records=8, compact_pitch=64)
+    assert (gres.code, gres.pos, gres.state, gres.byte) == (ores.code, ores.pos, ores.state, ores.byte)
+    import halo2_regex_b200 as H
+    assert H.compare_outputs(g, o) == []
+
+
 def test_long_string_invalid_transition():
     import torch
     import halo2_regex_b200 as H
