@@ -440,6 +440,53 @@ def test_config4_large_dfa():
     assert np.array_equal((g.status["flags"] & 1).astype(bool), plan["has_from"])
 
 
+@pytest.mark.parametrize("which,log2n", [("regex1", 20), ("three", 17), ("regex3_k3", 17), ("large_dfa", 15)])
+def test_large_batches_against_tiled_oracle(which, log2n):
+    """Sizes the oracle cannot walk in seconds: the batch is `base` distinct strings tiled N/base times, so every
+    multiplicity counter must be exactly N/base times the oracle's over the base strings (a checksum over all N*M rows),
+    and every column of a sample of rows (first, last and a few tiles in between) must equal the oracle's."""
+    import torch
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    from halo2_regex_b200 import workloads as W
+    base, N = 256, 1 << log2n
+    if which == "large_dfa":
+        L = 4096
+        allstr, substr, _ = W.large_dfa_texts()
+        cfg = H.RegexVerifyConfig.configure(L + 1, [H.RegexDefs(H.AllstrRegexDef.read_from_reader(allstr), [H.SubstrRegexDef.read_from_reader(substr)])])
+        ocfg = O.OracleConfig([(O.OracleAllstr(allstr), [O.OracleSubstr(substr)])], L + 1)
+        data, _ = W.config4_numpy(base, L)
+    else:
+        L = 1024
+        cfg, ocfg = product_config(which, L + 1), oracle_config(which, L + 1)
+        data, _ = W.config1_numpy(base, L) if which == "regex1" else W.config2_numpy(base, L)      # regex1, 2^20: BASELINE config 1 in full
+    M = L + 1
+    d_bytes = torch.from_numpy(data).cuda().repeat(N // base, 1).reshape(-1).contiguous()
+    d_offs = torch.arange(N + 1, dtype=torch.int64, device="cuda") * L
+    out = H.DeviceOutputs(cfg, N, compact_pitch=32, max_records=4)
+    cfg.match_batch_device(d_bytes, d_offs, out)
+    assert cfg.batch_result().code == 0
+    o, ores = ocfg.match_batch(data.reshape(-1), np.arange(base + 1, dtype=np.uint64) * L, max_records=4, compact_pitch=32)
+    assert ores.code == 0
+    for d in range(cfg.n_defs):
+        mult = out.mult[d].cpu().numpy().astype(np.uint64)
+        assert int(mult.sum()) == N * M
+        assert np.array_equal(mult, o.mult[d].astype(np.uint64) * np.uint64(N // base)), d
+        em = out.endpoint_mult[d].cpu().numpy().astype(np.uint64)
+        assert np.array_equal(em, o.endpoint_mult[d].astype(np.uint64) * np.uint64(N // base)), d
+    for t in (0, 1, N // base // 2, N // base - 1):          # tile t of the batch == the base strings again
+        lo = t * base
+        for d in range(cfg.n_defs):
+            assert np.array_equal(out.states[d][lo:lo + base, :M].cpu().numpy().view(o.states[d].dtype), o.states[d][:, :M]), (t, d)
+            assert np.array_equal(out.substr_ids[d][lo:lo + base, :M].cpu().numpy(), o.substr_ids[d][:, :M]), (t, d)
+            assert np.array_equal(out.start_enable[d][lo:lo + base].cpu().numpy()[:, :(M + 7) // 8], o.start_enable[d][:, :(M + 7) // 8]), (t, d)
+            assert np.array_equal(out.end_enable[d][lo:lo + base].cpu().numpy()[:, :(M + 7) // 8], o.end_enable[d][:, :(M + 7) // 8]), (t, d)
+        assert np.array_equal(out.masked_chars[lo:lo + base, :M].cpu().numpy(), o.masked_chars[:, :M]), t
+        assert np.array_equal(out.masked_substr_ids[lo:lo + base, :M].cpu().numpy(), o.masked_substr_ids[:, :M]), t
+        st = out.status[lo:lo + base].cpu().numpy().view(H._abi.STATUS_DTYPE).reshape(-1)
+        assert np.array_equal(st["flags"], o.status["flags"]), t
+
+
 def test_host_entry_point_slices():
     """b2r_match_batch_host cuts large batches into slices (H2D / kernels / D2H overlap on three streams): same bits, the
     multiplicities of the slices add up, and the batch result is the lowest failing string over all slices."""
