@@ -387,6 +387,28 @@ def test_long_string_host_entry_point(set_name, length):
     assert H.compare_outputs(g, o) == []
 
 
+def test_long_string_16_mib_bit_exact():
+    """A quarter of BASELINE config 3 (one 16 MiB string, 16 385 chunks, three tree levels) against the oracle, every column."""
+    import halo2_regex_b200 as H
+    rng = np.random.default_rng(0xB2000003)
+    length = 1 << 24
+    alphabet = np.array([9, 10, 13] + list(range(32, 127)), dtype=np.uint8)
+    body = alphabet[rng.integers(0, len(alphabet), length)]
+    plant = np.frombuffer(b" Also for xyzzy.", dtype=np.uint8)
+    for at in [0, 1013, 1020, 65530, (1 << 22) - 7, length - len(plant)] + list(rng.integers(0, length - 64, 200)):
+        body[at:at + len(plant)] = plant                       # some straddle chunk and tree-node boundaries
+    s = body.tobytes()
+    M = length + 1
+    cfg = product_config("regex2", 64)
+    ocfg = oracle_config("regex2", M)
+    g, gres = cfg.match_long_host(s, check=False, max_records=8, compact_pitch=64)
+    data, offs = _pack([s])
+    o, ores = ocfg.match_batch(data, offs, max_records=8, compact_pitch=64)
+    assert gres.code == ores.code == 0
+    assert H.compare_outputs(g, o) == []
+    assert int(g.mult[0].sum()) == M
+
+
 def test_long_string_invalid_transition():
     import torch
     import halo2_regex_b200 as H
