@@ -249,13 +249,14 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             const uint32_t s = cur >> NSH;
             if (s < p.def[d].num_states) {
                 const uint32_t key = ((s << 8) | c) + 1u;
-                const uint32_t slot = hist_s[d] + (((key * 0x9E3779B1u) >> (32 - cache_log2)) << 3);
+                // keys and counts in two arrays (not {key, count} pairs: those would put every key in an even bank)
+                const uint32_t slot = hist_s[d] + (((key * 0x9E3779B1u) >> (32 - cache_log2)) << 2);
                 uint32_t owner = lds32(slot);
                 if (owner == 0) {
                     asm volatile("atom.shared.cas.b32 %0, [%1], 0, %2;" : "=r"(owner) : "r"(slot), "r"(key) : "memory");
                     if (owner == 0) owner = key;
                 }
-                if (owner == key) red_shared_inc(slot + 4);
+                if (owner == key) red_shared_inc(slot + (4u << cache_log2));
                 else atomicAdd(p.def[d].hist + (size_t)c * p.def[d].num_states + s, 1ull);
             }
         }
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         for (int d = 0; d < D; d++) {
             const uint32_t S = p.def[d].num_states;
             for (uint32_t i = threadIdx.x; i < (1u << cache_log2); i += blockDim.x) {
-                const uint32_t key = lds32(hist_s[d] + i * 8), v = lds32(hist_s[d] + i * 8 + 4);
+                const uint32_t key = lds32(hist_s[d] + i * 4), v = lds32(hist_s[d] + (4u << cache_log2) + i * 4);
                 if (key && v) atomicAdd(p.def[d].hist + (size_t)((key - 1) & 255u) * S + ((key - 1) >> 8), (unsigned long long)v);
             }
         }
