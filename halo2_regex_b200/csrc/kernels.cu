@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "emit.cuh"
 #include "walk.cuh"
@@ -81,7 +82,9 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     };
     // HIST_GLOBAL: the largest bin cache (4096 .. 256 slots per def) that leaves room for the warps
     auto fits = [&](uint32_t tm, uint32_t hm, int warps) {
-        for (p.hist_cache_log2 = 12; p.hist_cache_log2 >= 8; p.hist_cache_log2--)
+        uint32_t top = 12;
+        if (const char* e = getenv("B2R_HIST_CACHE_LOG2")) { const int v = atoi(e); if (v >= 8 && v <= 14) top = (uint32_t)v; }   // tuning hook
+        for (p.hist_cache_log2 = top; p.hist_cache_log2 >= 8; p.hist_cache_log2--)
             if (fits_k(tm, hm, warps)) return true;
         p.hist_cache_log2 = 8;
         return false;
