@@ -699,6 +699,23 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
         lp.def[d].num_classes = c->packed[d].num_classes;
         lp.def[d].maps = (uint16_t*)(ws + off_maps[d]); lp.def[d].entry = (uint16_t*)(ws + off_entry[d]);
     }
+    // the sparse columns are zeroed on a side stream while the (latency-bound) prefix stages and the walk run; joined before
+    // the emit stage
+    {
+        cudaStream_t zs = c->in_stream;
+        CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(zs, c->ev_fork, 0));
+        auto zero = [&](void* ptr, size_t bytes) { return ptr ? cudaMemsetAsync(ptr, 0, bytes, zs) : cudaSuccess; };
+        const size_t col_bytes = align_up(M, 16), bm_bytes = align_up((M + 7) / 8, 4);
+        for (uint32_t d = 0; d < c->n_defs; d++) {
+            CUDA_TRY(zero(o->substr_ids[d], col_bytes));
+            CUDA_TRY(zero(o->start_enable[d], bm_bytes));
+            CUDA_TRY(zero(o->end_enable[d], bm_bytes));
+        }
+        CUDA_TRY(zero(o->masked_chars, col_bytes));
+        CUDA_TRY(zero(o->masked_substr_ids, col_bytes));
+        CUDA_TRY(cudaEventRecord(c->ev_done[0], zs));
+    }
     if ((rc = launch_long_prepare(lp, st, &c->last_launches))) return rc;
 
     // ---- 3: the walk, chunk = string, one contiguous state row ------------------------------------------------------------
@@ -718,16 +735,8 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     c->last_launches++;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
 
-    // ---- 4: zero the sparse columns, then the ordered emit stage of the one string ---------------------------------------------
-    auto zero = [&](void* ptr, size_t bytes) { return ptr ? cudaMemsetAsync(ptr, 0, bytes, st) : cudaSuccess; };
-    const size_t col_bytes = align_up(M, 16), bm_bytes = align_up((M + 7) / 8, 4);
-    for (uint32_t d = 0; d < c->n_defs; d++) {
-        CUDA_TRY(zero(o->substr_ids[d], col_bytes));
-        CUDA_TRY(zero(o->start_enable[d], bm_bytes));
-        CUDA_TRY(zero(o->end_enable[d], bm_bytes));
-    }
-    CUDA_TRY(zero(o->masked_chars, col_bytes));
-    CUDA_TRY(zero(o->masked_substr_ids, col_bytes));
+    // ---- 4: the ordered emit stage of the one string (sparse columns zeroed by now) --------------------------------------------
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[0], 0));
     WalkParams& pe = c->last;
     fill_walk_params(c, pe, d_bytes, d_offsets + n_chunks + 1, 1, len, o, M);
     pe.fuse = 0; pe.prefilled = 1;
