@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 
     const WalkLayout lay = walk_layout(p, SB);
     const uint32_t base_s = (smem_u32(dsmem) + lay.align - 1) & ~(lay.align - 1);
+    // bytes per zero-fill op: smaller ops spread more evenly over the chunk loop (one def: 58 ops of 2 KB, two per lane;
+    // 1.45 -> 1.43 ms on config 1; 8 KB ops: 1.50 ms), but a lane defers at most two, so more defs keep 4 KB ops
+    constexpr uint32_t ZOP = D == 1 ? 2048u : WALK_ZERO_BYTES;
     constexpr bool E16 = TM == (int)TABLE_PLAIN16;                       // 16-bit entries: next << 1 | rare (else next << 16 | next * stride | rare)
     constexpr uint32_t NSH = E16 ? 1u : 16u;                            // entry >> NSH = the state
     constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             uint32_t total_ops = 0;
 #pragma unroll
             for (int r = 0; r < 3 * D + 2; r++)
-                if (reg_ptr[r]) total_ops += ((uint32_t)(reg_bytes[r] & ~15ull) + WALK_ZERO_BYTES - 1) / WALK_ZERO_BYTES;
+                if (reg_ptr[r]) total_ops += ((uint32_t)(reg_bytes[r] & ~15ull) + ZOP - 1) / ZOP;
             const bool spread = p.spread_fill && n_chunks > 1;
             const uint32_t sched_den = total_ops > n_chunks ? total_ops : n_chunks;
             uint32_t first = 0;
@@ -343,10 +346,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             for (int r = 0; r < 3 * D + 2; r++) {
                 if (!reg_ptr[r]) continue;
                 const uint32_t bulk_bytes = (uint32_t)(reg_bytes[r] & ~15ull);   // bitmap regions of a partial tile can end on a 4-byte boundary
-                const uint32_t n_ops = (bulk_bytes + WALK_ZERO_BYTES - 1) / WALK_ZERO_BYTES;
+                const uint32_t n_ops = (bulk_bytes + ZOP - 1) / ZOP;
                 for (uint32_t op = (lane + 32u - (first & 31u)) & 31u; op < n_ops; op += 32) {
-                    const uint32_t o = op * WALK_ZERO_BYTES;
-                    const uint32_t nb = bulk_bytes - o < WALK_ZERO_BYTES ? bulk_bytes - o : WALK_ZERO_BYTES;
+                    const uint32_t o = op * ZOP;
+                    const uint32_t nb = bulk_bytes - o < ZOP ? bulk_bytes - o : ZOP;
                     const uint32_t j = first + op;                      // j % 32 == lane
                     if (spread && j < 64) {
                         const uint32_t at = j * n_chunks / sched_den;
