@@ -5,7 +5,7 @@ Importing this package loads halo2_regex_b200/libb2r.so and fails loudly if it h
 """
 from . import _abi  # noqa: F401
 from ._ffi import LIB_PATH, SYMBOLS, last_error, lib  # noqa: F401
-from .buffers import HostOutputs, compare_outputs  # noqa: F401
+from .buffers import HostOutputs, PinnedAllocator, compare_outputs  # noqa: F401
 from .defs import AllstrRegexDef, RegexDefs, RegexParseError, SubstrRegexDef  # noqa: F401
 from .regex import (AssignedRegexResult, DeviceOutputs, InvalidTransitionError, RegexVerifyConfig,  # noqa: F401
                     StringTooLongError)

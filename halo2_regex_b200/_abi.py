@@ -20,6 +20,7 @@ B2R_ST_RECORDS_TRUNCATED = 1 << 11
 B2R_ST_COMPACT_TRUNCATED = 1 << 12
 
 B2R_OUT_ACCUMULATE_MULT = 1
+B2R_OUT_SPARSE_D2H = 2
 
 
 def B2R_ST_ACCEPTED(d):

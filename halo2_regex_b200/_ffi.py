@@ -24,6 +24,8 @@ b2r_config_dummy_state b2r_config_substr_id_offset b2r_config_num_byte_classes b
 b2r_config_recommended_bitmap_pitch b2r_table_num_rows b2r_table_rows b2r_endpoint_num_rows b2r_endpoint_rows
 b2r_match_batch b2r_batch_result b2r_match_batch_host b2r_match_substrs b2r_match_long b2r_match_long_host b2r_last_launch_count
 b2r_config_set_timing b2r_last_kernel_ms b2r_last_stage_ms b2r_last_plan
+b2r_config_new_multi b2r_config_num_devices b2r_config_set_option b2r_host_alloc b2r_host_free b2r_host_register b2r_host_unregister
+b2r_last_host_bytes
 """.split()
 
 
@@ -84,6 +86,14 @@ def _load():
     sig("b2r_last_kernel_ms", i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float))
     sig("b2r_last_stage_ms", i32, vp, C.POINTER(C.c_float))
     sig("b2r_last_plan", i32, vp, C.POINTER(u32), C.POINTER(u32))
+    sig("b2r_config_new_multi", i32, pvp, C.POINTER(pvp), C.POINTER(u32), u32, u64, C.POINTER(i32), u32, pvp)
+    sig("b2r_config_num_devices", u32, vp)
+    sig("b2r_config_set_option", i32, vp, C.c_char_p, C.c_char_p)
+    sig("b2r_host_alloc", i32, sz, pvp)
+    sig("b2r_host_free", i32, vp)
+    sig("b2r_host_register", i32, vp, sz)
+    sig("b2r_host_unregister", i32, vp)
+    sig("b2r_last_host_bytes", i32, vp, pu64, pu64)
     return L
 
 

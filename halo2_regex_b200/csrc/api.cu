@@ -1,4 +1,5 @@
-// extern "C" boundary (include/b2r.h): handles, table queries, the batch entry points.
+// extern "C" boundary (include/b2r.h): handles, table queries, the device-pointer batch entry points.  The host-pointer entry
+// points live in host.cu.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -10,94 +11,12 @@
 #include <string>
 #include <vector>
 
-#include "../../include/b2r.h"
-#include "defs.hpp"
-#include "kernels.cuh"
+#include "config.hpp"
 #include "long.cuh"
 
 using namespace b2r;
 
-struct b2r_allstr { AllstrDef def; };
-struct b2r_substr { SubstrDef def; };
-
-#define CUDA_TRY(expr)                                                                   \
-    do {                                                                                 \
-        cudaError_t _e = (expr);                                                         \
-        if (_e != cudaSuccess) {                                                         \
-            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                   \
-            return B2R_ERR_CUDA;                                                         \
-        }                                                                                \
-    } while (0)
-
 namespace {
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t n) {
-        if (n <= cap) return B2R_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        CUDA_TRY(cudaMalloc(&p, n));
-        cap = n;
-        return B2R_OK;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct DevDef {
-    uint8_t* byte_class = nullptr;
-    uint32_t* trans = nullptr;
-    uint32_t* hot = nullptr;     // walk table [C][P] (walk.cuh)
-    uint32_t *row_bin = nullptr, *erow_start_bin = nullptr, *erow_end_bin = nullptr;
-    unsigned long long *hist = nullptr, *ep_start = nullptr, *ep_end = nullptr;  // inside cfg->scratch
-};
-
-}  // namespace
-
-struct b2r_config {
-    int device = -1;             // -1: host-only handle (table queries), no matching
-    uint64_t max_chars = 0;
-    uint32_t n_defs = 0;
-    PackedDef packed[B2R_MAX_DEFS];
-    DevDef dev[B2R_MAX_DEFS];
-    void* tables = nullptr;      // one allocation holding every constant table
-    void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
-    size_t scratch_bytes = 0;
-    b2r_batch_status* d_batch_status = nullptr;
-    int force_table_mode = -1;        // testing hooks: B2R_TABLE_MODE=repl|plain|global, B2R_HIST_MODE=smem|global
-    int force_hist_mode = -1;
-    DevBuf ws_fmask;                  // granule flags (walk -> emit)
-    DevBuf ws_long;                   // long-string path: chunk offsets, transition-vector tree, entry states, flag summary
-    DevBuf ws_states[B2R_MAX_DEFS];   // state column of a def the caller did not ask for (emit reads it)
-    WalkParams last = {};
-    bool have_last = false;
-    uint32_t last_launches = 0;
-    bool timing = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before walk, after walk, after emit, after finalize
-    // staging for the host-pointer entry point
-    DevBuf ws_bytes, ws_offsets, ws_cols;
-    cudaStream_t host_stream = nullptr;
-    cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host entry point: H2D / D2H copies overlapping the kernels
-    static constexpr int MAX_SLICES = 8;
-    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
-    BatchCounters* h_slices = nullptr;    // pinned: the counters of every slice of a host batch
-    cudaEvent_t ev_fork = nullptr;
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int upload_tables(b2r_config* c) {
     size_t total = 0;
@@ -109,9 +28,10 @@ int upload_tables(b2r_config* c) {
     CUDA_TRY(cudaMalloc(&c->tables, total));
     unsigned char* base = (unsigned char*)c->tables;
     size_t off = 0;
+    cudaError_t put_err = cudaSuccess;                                    // first failing upload
     auto put = [&](const void* src, size_t n) -> void* {
         void* dst = base + off;
-        cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+        if (n) { const cudaError_t e = cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); if (e != cudaSuccess && put_err == cudaSuccess) put_err = e; }
         off += align_up(n, 256);
         return dst;
     };
@@ -130,6 +50,7 @@ int upload_tables(b2r_config* c) {
         c->dev[d].erow_end_bin = (uint32_t*)put(pd.erow_end_bin.data(), pd.erows.size() * 4);
         scratch += align_up((size_t)256 * pd.num_states * 8, 256) + 2 * align_up((size_t)std::max<uint32_t>(pd.num_substrs, 1) * pd.num_states * 8, 256);
     }
+    if (put_err != cudaSuccess) { set_error("uploading the packed tables failed: %s", cudaGetErrorString(put_err)); return B2R_ERR_CUDA; }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMalloc(&c->scratch, scratch));
     c->scratch_bytes = scratch;
@@ -143,16 +64,34 @@ int upload_tables(b2r_config* c) {
         c->dev[d].ep_end = (unsigned long long*)(sb + so); so += ep;
     }
     CUDA_TRY(cudaMalloc((void**)&c->d_batch_status, sizeof(b2r_batch_status)));
-    if (const char* tm = getenv("B2R_TABLE_MODE"))
-        c->force_table_mode = !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "plain16") ? (int)TABLE_PLAIN16 : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
-    if (const char* hm = getenv("B2R_HIST_MODE"))
-        c->force_hist_mode = !strcmp(hm, "smem") ? (int)HIST_SMEM : !strcmp(hm, "global") ? (int)HIST_GLOBAL : -1;
     return B2R_OK;
 }
 
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+int parse_table_mode(const char* tm) {
+    return !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "plain16") ? (int)TABLE_PLAIN16 : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
+}
+int parse_hist_mode(const char* hm) { return !strcmp(hm, "smem") ? (int)HIST_SMEM : !strcmp(hm, "global") ? (int)HIST_GLOBAL : -1; }
 
-int check_outputs(const b2r_config* c, const b2r_outputs* o, bool check_ptrs, uint64_t M = 0) {
+// the environment is consulted once per handle, never on the batch path
+void read_env_options(b2r_config* c) {
+    auto& o = c->opt;
+    if (const char* e = getenv("B2R_TABLE_MODE")) o.force_table_mode = parse_table_mode(e);
+    if (const char* e = getenv("B2R_HIST_MODE")) o.force_hist_mode = parse_hist_mode(e);
+    if (const char* e = getenv("B2R_DEBUG")) o.debug = (uint32_t)atoi(e);
+    if (const char* e = getenv("B2R_SPREAD_FILL")) o.spread_fill = e[0] == '0' ? 0u : 1u;
+    if (const char* e = getenv("B2R_FUSE")) o.fuse = e[0] == '0' ? 0u : 1u;
+    if (const char* e = getenv("B2R_SLICES")) o.slices = atoi(e);
+    o.trace_host = getenv("B2R_TRACE_HOST") != nullptr;
+    if (const char* e = getenv("B2R_HIST_CACHE_LOG2")) o.hist_cache_log2 = atoi(e);
+    if (const char* e = getenv("B2R_HOST_THREADS")) o.host_threads = atoi(e);
+    if (const char* e = getenv("B2R_SMALL_PATH")) o.small_path = atoi(e);
+}
+
+}  // namespace
+
+namespace b2r {
+
+int check_outputs(const b2r_config* c, const b2r_outputs* o, bool check_ptrs, uint64_t M) {
     if (!M) M = c->max_chars;
     if (o->row_pitch < M || o->row_pitch % 16) { set_error("row_pitch %llu must be >= max_chars_size and a multiple of 16", (unsigned long long)o->row_pitch); return B2R_ERR_ALIGNMENT; }
     if (o->bitmap_pitch < (M + 7) / 8 || o->bitmap_pitch % 4) { set_error("bitmap_pitch %llu must be >= ceil(M/8) and a multiple of 4", (unsigned long long)o->bitmap_pitch); return B2R_ERR_ALIGNMENT; }
@@ -186,9 +125,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
-    { const char* dbg = getenv("B2R_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
-    { const char* f = getenv("B2R_SPREAD_FILL"); p.spread_fill = (f && f[0] == '0') ? 0u : 1u; }   // testing hook
-    { const char* f = getenv("B2R_FUSE"); p.fuse = (f && f[0] == '0') ? 0u : 1u; }   // testing hook: B2R_FUSE=0 runs emit_kernel as its own launch
+    p.debug = c->opt.debug; p.spread_fill = c->opt.spread_fill; p.fuse = c->opt.fuse;
     p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;
@@ -203,7 +140,7 @@ int enqueue_finalize(b2r_config* c, const b2r_outputs* o, uint64_t n, uint64_t m
     FinalizeParams f;
     memset(&f, 0, sizeof f);
     f.n_defs = c->n_defs; f.accumulate = (o->flags & B2R_OUT_ACCUMULATE_MULT) ? 1 : 0;
-    f.n_rows_total = n * max_chars; f.counters = (const BatchCounters*)c->scratch;
+    f.n_rows_total = n * max_chars; f.counters = (const BatchCounters*)c->scratch; f.counters_copy = c->counters_copy;
     bool any = false;
     for (uint32_t d = 0; d < c->n_defs; d++) {
         auto& fd = f.def[d];
@@ -213,12 +150,65 @@ int enqueue_finalize(b2r_config* c, const b2r_outputs* o, uint64_t n, uint64_t m
         fd.mult = (unsigned long long*)o->mult[d]; fd.endpoint_mult = (unsigned long long*)o->endpoint_mult[d];
         any = any || fd.mult || fd.endpoint_mult;
     }
-    if (!any) return B2R_OK;
+    if (!any && !f.counters_copy) return B2R_OK;
     c->last_launches++;
     return launch_finalize(f, st);
 }
 
-}  // namespace
+// ---- the hot call ------------------------------------------------------------------------------------------------------
+int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+                            const b2r_outputs* o, uint64_t max_chars, cudaStream_t st) {
+    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
+    if (!o || (n && (!d_bytes && total_bytes)) || (n && !d_offsets)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (!aligned16(d_bytes)) { set_error("bytes must be 16-byte aligned"); return B2R_ERR_ALIGNMENT; }
+    int rc = check_outputs(c, o, true);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
+    c->last_launches = 0;
+    CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
+    WalkParams& p = c->last;
+    fill_walk_params(c, p, d_bytes, d_offsets, n, total_bytes, o, max_chars);
+    c->have_last = true;
+    bool wide = false;
+    for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
+    if (n) {
+        // walk -> emit hand-over: granule flags, and a scratch state column for every def the caller does not want
+        if ((rc = c->ws_fmask.reserve(std::max<size_t>((size_t)p.fm_words * n * 4, 16)))) return rc;
+        p.fmask = (uint32_t*)c->ws_fmask.p;
+        for (uint32_t d = 0; d < c->n_defs; d++) {
+            if (p.def[d].states) continue;
+            if ((rc = c->ws_states[d].reserve((size_t)n * o->row_pitch * (wide ? 2 : 1)))) return rc;
+            p.def[d].states = c->ws_states[d].p;
+        }
+        if ((rc = plan_walk(p, wide, c->opt.force_table_mode, c->opt.force_hist_mode, c->opt.hist_cache_log2))) return rc;
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
+    if (n) {
+        if ((rc = launch_walk(p, wide, st, nullptr))) return rc;
+        c->last_launches++;
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
+    if (n && !p.fuse) {
+        if ((rc = launch_emit(p, wide, st, nullptr))) return rc;
+        c->last_launches++;
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    rc = enqueue_finalize(c, o, n, max_chars, st);
+    if (rc) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], st));
+    return B2R_OK;
+}
+
+void report_failure(const b2r_batch_status& r) {
+    if (r.code == B2R_ERR_INVALID_TRANSITION)
+        set_error("The transition from %u by %u is invalid! (string %llu, position %u, def %u)", r.state, (unsigned)r.byte,
+                  (unsigned long long)r.string_idx, r.pos, (unsigned)r.def);
+    else if (r.code == B2R_ERR_TOO_LONG)
+        set_error("string %llu is longer than max_chars_size-1 (or its offsets leave the byte buffer)", (unsigned long long)r.string_idx);
+}
+
+}  // namespace b2r
 
 extern "C" {
 
@@ -229,6 +219,7 @@ const char* b2r_version(void) { return "b2r 0.1 (sm_100a)"; }
 int b2r_allstr_parse(const char* text, size_t len, b2r_allstr** out, uint64_t* err_line) {
     if (!out || (!text && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
     std::unique_ptr<b2r_allstr> a(new (std::nothrow) b2r_allstr);
+    if (!a) { set_error("out of memory"); return B2R_ERR_INVALID_ARG; }
     int rc = parse_allstr(text, len, a->def, err_line);
     if (rc) return rc;
     *out = a.release();
@@ -263,6 +254,7 @@ int b2r_allstr_entries(const b2r_allstr* a, uint64_t* out4, uint64_t capacity_ro
 int b2r_substr_parse(const char* text, size_t len, b2r_substr** out, uint64_t* err_line) {
     if (!out || (!text && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
     std::unique_ptr<b2r_substr> s(new (std::nothrow) b2r_substr);
+    if (!s) { set_error("out of memory"); return B2R_ERR_INVALID_ARG; }
     int rc = parse_substr(text, len, s->def, err_line);
     if (rc) return rc;
     *out = s.release();
@@ -278,6 +270,7 @@ int b2r_substr_new(uint64_t max_length, uint64_t min_position, uint64_t max_posi
                    const uint64_t* start_states, uint64_t n_start, const uint64_t* end_states, uint64_t n_end, b2r_substr** out) {
     if (!out) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
     std::unique_ptr<b2r_substr> s(new (std::nothrow) b2r_substr);
+    if (!s) { set_error("out of memory"); return B2R_ERR_INVALID_ARG; }
     s->def.max_length = max_length; s->def.min_position = min_position; s->def.max_position = max_position;
     for (uint64_t i = 0; i < n_pairs; i++) s->def.valid_state_transitions.insert({pairs[2 * i], pairs[2 * i + 1]});
     s->def.start_states.assign(start_states, start_states + n_start);
@@ -316,8 +309,12 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
     if (!allstr || !n_substrs || !out || n_defs == 0) { set_error("null / empty argument"); return B2R_ERR_INVALID_ARG; }
     if (n_defs > B2R_MAX_DEFS) { set_error("%u regex defs: at most %d are supported", n_defs, B2R_MAX_DEFS); return B2R_ERR_UNSUPPORTED; }
     if (max_chars_size == 0 || max_chars_size > 0xFFFFFFF0ull) { set_error("max_chars_size out of range"); return B2R_ERR_INVALID_ARG; }
-    std::unique_ptr<b2r_config> c(new (std::nothrow) b2r_config);
-    c->n_defs = n_defs; c->max_chars = max_chars_size; c->device = device;
+    // every error path below releases what was created so far (device tables, streams, events, pinned memory)
+    struct Free { void operator()(b2r_config* p) const { b2r_config_free(p); } };
+    std::unique_ptr<b2r_config, Free> c(new (std::nothrow) b2r_config);
+    if (!c) { set_error("out of memory"); return B2R_ERR_INVALID_ARG; }
+    read_env_options(c.get());
+    c->n_defs = n_defs; c->max_chars = max_chars_size; c->device = -1;   // bound to the device once it has been validated
     uint32_t offset = 1;  // src/lib.rs:780, 827
     uint64_t max_sum = 0;
     for (uint32_t d = 0; d < n_defs; d++) {
@@ -344,13 +341,16 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return B2R_ERR_CUDA; }
         DeviceGuard g(device);
         if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B2R_ERR_CUDA; }
+        c->device = device;
         int rc = upload_tables(c.get());
         if (rc) return rc;
         CUDA_TRY(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->pay_stream, cudaStreamNonBlocking));
         for (auto& e : c->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_pay) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaMallocHost((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -361,17 +361,22 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
 
 void b2r_config_free(b2r_config* c) {
     if (!c) return;
+    if (c->multi) { multi_free(c->multi); c->multi = nullptr; }
+    c->pool.reset();                                                       // joins the host worker threads
     if (c->device >= 0) {
         DeviceGuard g(c->device);
         cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
         c->ws_fmask.release(); c->ws_long.release();
         for (auto& b : c->ws_states) b.release();
-        c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release();
+        c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release(); c->ws_sparse.release();
+        c->pin_sparse.release(); c->pin_small.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         if (c->in_stream) cudaStreamDestroy(c->in_stream);
         if (c->out_stream) cudaStreamDestroy(c->out_stream);
+        if (c->pay_stream) cudaStreamDestroy(c->pay_stream);
         for (auto& e : c->ev_in) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_done) if (e) cudaEventDestroy(e);
+        for (auto& e : c->ev_pay) if (e) cudaEventDestroy(e);
         if (c->h_slices) cudaFreeHost(c->h_slices);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -403,53 +408,6 @@ int b2r_endpoint_rows(const b2r_config* c, uint32_t d, uint64_t* out3, uint64_t 
     return B2R_OK;
 }
 
-// ---- the hot call ------------------------------------------------------------------------------------------------------
-static int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
-                            const b2r_outputs* o, uint64_t max_chars, cudaStream_t st) {
-    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
-    if (!o || (n && (!d_bytes && total_bytes)) || (n && !d_offsets)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
-    if (!aligned16(d_bytes)) { set_error("bytes must be 16-byte aligned"); return B2R_ERR_ALIGNMENT; }
-    int rc = check_outputs(c, o, true);
-    if (rc) return rc;
-    DeviceGuard g(c->device);
-    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
-    c->last_launches = 0;
-    CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none
-    WalkParams& p = c->last;
-    fill_walk_params(c, p, d_bytes, d_offsets, n, total_bytes, o, max_chars);
-    c->have_last = true;
-    bool wide = false;
-    for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
-    for (uint32_t d = 0; d < c->n_defs; d++)
-    if (n) {
-        // walk -> emit hand-over: granule flags, and a scratch state column for every def the caller does not want
-        if ((rc = c->ws_fmask.reserve(std::max<size_t>((size_t)p.fm_words * n * 4, 16)))) return rc;
-        p.fmask = (uint32_t*)c->ws_fmask.p;
-        for (uint32_t d = 0; d < c->n_defs; d++) {
-            if (p.def[d].states) continue;
-            if ((rc = c->ws_states[d].reserve((size_t)n * o->row_pitch * (wide ? 2 : 1)))) return rc;
-            p.def[d].states = c->ws_states[d].p;
-        }
-        if ((rc = plan_walk(p, wide, c->force_table_mode, c->force_hist_mode))) return rc;
-    }
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
-    if (n) {
-        if ((rc = launch_walk(p, wide, st, nullptr))) return rc;
-        c->last_launches++;
-    }
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
-    if (n && !p.fuse) {
-        if ((rc = launch_emit(p, wide, st, nullptr))) return rc;
-        c->last_launches++;
-    }
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
-    rc = enqueue_finalize(c, o, n, max_chars, st);
-    if (rc) return rc;
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], st));
-    return B2R_OK;
-}
-
 int b2r_match_batch(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
                     const b2r_outputs* d_out, void* cuda_stream) {
     if (!c) { set_error("null config"); return B2R_ERR_INVALID_ARG; }
@@ -466,187 +424,15 @@ int b2r_batch_result(b2r_config* c, void* cuda_stream, b2r_batch_status* out) {
     b2r_batch_status r;
     memset(&r, 0, sizeof r);
     r.n_overlap_lo = (uint32_t)h.n_overlap;
-    if (h.first_bad != ~0ull) {
-        int rc = launch_diagnose(c->last, h.first_bad, c->d_batch_status, st);
+    if (h.any_bad()) {
+        int rc = launch_diagnose(c->last, h.first_bad(), c->d_batch_status, st);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaMemcpy(&r, c->d_batch_status, sizeof r, cudaMemcpyDeviceToHost));
-        if (r.code == B2R_ERR_INVALID_TRANSITION)
-            set_error("The transition from %u by %u is invalid! (string %llu, position %u, def %u)", r.state, (unsigned)r.byte,
-                      (unsigned long long)r.string_idx, r.pos, (unsigned)r.def);
-        else if (r.code == B2R_ERR_TOO_LONG)
-            set_error("string %llu is longer than max_chars_size-1", (unsigned long long)r.string_idx);
+        report_failure(r);
     }
     if (out) *out = r;
     return r.code;
-}
-
-// ---- host-pointer entry point ----------------------------------------------------------------------------------------
-int b2r_match_batch_host(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets, uint64_t n, const b2r_outputs* ho,
-                         b2r_batch_status* result) {
-    if (!c || !ho || (n && !h_offsets)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
-    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
-    int rc = check_outputs(c, ho, false);  // same pitches are used on the device; host pointer alignment is irrelevant
-    if (rc) return rc;
-    DeviceGuard g(c->device);
-    cudaStream_t st = c->host_stream;
-    const uint64_t total = n ? h_offsets[n] : 0;
-    const uint64_t base = n ? h_offsets[0] : 0;
-    if (total < base) { set_error("offsets must be non-decreasing"); return B2R_ERR_INVALID_ARG; }
-    const uint64_t nbytes = total - base;
-    if ((rc = c->ws_bytes.reserve(align_up(nbytes + 16, 256)))) return rc;
-    if ((rc = c->ws_offsets.reserve((n + 1) * 8))) return rc;
-    // device columns, same layout as the host ones
-    const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
-    size_t need = 0;
-    auto slot = [&](size_t bytes) { size_t o = need; need += align_up(bytes, 256); return o; };
-    // stride: bytes per string (0: not per string).  pinned: page-locked destination, the copy is asynchronous; a copy into
-    // pageable memory blocks the calling thread until everything queued before it on its stream is done, so those are
-    // issued after the last slice instead of inside the pipeline (they would serialise the H2D of slice i+1 behind the
-    // D2H of slice i: measured 110 ms instead of 92 ms per 2^20-string batch with three small pageable columns).
-    struct Copy { size_t off; void* host; size_t bytes; size_t stride; bool pinned; };
-    auto is_pinned = [](const void* h) {
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost;
-    };
-    std::vector<Copy> copies;
-    b2r_outputs dout = *ho;
-    size_t off_states[B2R_MAX_DEFS], off_sid[B2R_MAX_DEFS], off_se[B2R_MAX_DEFS], off_ee[B2R_MAX_DEFS], off_mult[B2R_MAX_DEFS], off_em[B2R_MAX_DEFS];
-    for (uint32_t d = 0; d < c->n_defs; d++) {
-        const size_t w = c->packed[d].state_width;
-        off_states[d] = ho->states[d] ? slot(n * rp * w) : 0;
-        off_sid[d] = ho->substr_ids[d] ? slot(n * rp) : 0;
-        off_se[d] = ho->start_enable[d] ? slot(n * bp) : 0;
-        off_ee[d] = ho->end_enable[d] ? slot(n * bp) : 0;
-        off_mult[d] = ho->mult[d] ? slot(c->packed[d].rows.size() * 8) : 0;
-        off_em[d] = ho->endpoint_mult[d] ? slot(c->packed[d].erows.size() * 16) : 0;
-    }
-    const size_t off_mc = ho->masked_chars ? slot(n * rp) : 0, off_ms = ho->masked_substr_ids ? slot(n * rp) : 0;
-    const size_t off_st = ho->status ? slot(n * sizeof(b2r_string_status)) : 0;
-    const size_t off_rec = ho->records ? slot(n * (size_t)ho->max_records * sizeof(b2r_substr_record)) : 0;
-    const size_t off_cb = ho->compact_bytes ? slot(n * (size_t)ho->compact_pitch) : 0;
-    if ((rc = c->ws_cols.reserve(need + 256))) return rc;
-    unsigned char* cb = (unsigned char*)c->ws_cols.p;
-    auto bind = [&](void* host, size_t off, size_t bytes, size_t stride = 0) -> void* {
-        if (!host) return nullptr;
-        copies.push_back({off, host, bytes, stride, is_pinned(host)});
-        return cb + off;
-    };
-    const bool acc = (ho->flags & B2R_OUT_ACCUMULATE_MULT) != 0;
-    for (uint32_t d = 0; d < c->n_defs; d++) {
-        const size_t w = c->packed[d].state_width;
-        dout.states[d] = bind(ho->states[d], off_states[d], n * rp * w, rp * w);
-        dout.substr_ids[d] = (uint8_t*)bind(ho->substr_ids[d], off_sid[d], n * rp, rp);
-        dout.start_enable[d] = (uint8_t*)bind(ho->start_enable[d], off_se[d], n * bp, bp);
-        dout.end_enable[d] = (uint8_t*)bind(ho->end_enable[d], off_ee[d], n * bp, bp);
-        dout.mult[d] = (uint64_t*)bind(ho->mult[d], off_mult[d], c->packed[d].rows.size() * 8);
-        dout.endpoint_mult[d] = (uint64_t*)bind(ho->endpoint_mult[d], off_em[d], c->packed[d].erows.size() * 16);
-        if (acc) {
-            if (ho->mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.mult[d], ho->mult[d], c->packed[d].rows.size() * 8, cudaMemcpyHostToDevice, st));
-            if (ho->endpoint_mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.endpoint_mult[d], ho->endpoint_mult[d], c->packed[d].erows.size() * 16, cudaMemcpyHostToDevice, st));
-        }
-    }
-    dout.masked_chars = (uint8_t*)bind(ho->masked_chars, off_mc, n * rp, rp);
-    dout.masked_substr_ids = (uint8_t*)bind(ho->masked_substr_ids, off_ms, n * rp, rp);
-    dout.status = (b2r_string_status*)bind(ho->status, off_st, n * sizeof(b2r_string_status), sizeof(b2r_string_status));
-    dout.records = (b2r_substr_record*)bind(ho->records, off_rec, n * (size_t)ho->max_records * sizeof(b2r_substr_record), (size_t)ho->max_records * sizeof(b2r_substr_record));
-    dout.compact_bytes = (uint8_t*)bind(ho->compact_bytes, off_cb, n * (size_t)ho->compact_pitch, (size_t)ho->compact_pitch);
-
-    // The batch is cut into slices of strings: the H2D copy of slice i+1 and the D2H copy of slice i-1 run on their own
-    // streams while the kernels of slice i run (PCIe is full duplex; the copies are the end-to-end bottleneck).
-    // inputs: keep the caller's offsets (the kernel adds them to the base pointer, so shift the base instead):
-    // d_bytes + offsets[j] must address string j: d_bytes = ws + (base & 15) - base  (16-byte aligned by construction)
-    unsigned char* const d_in = (unsigned char*)c->ws_bytes.p + (base & 15);
-    const uint8_t* d_bytes = d_in - base;
-    const uint64_t* d_offsets = (const uint64_t*)c->ws_offsets.p;
-    int n_slices = n >= 16384 ? b2r_config::MAX_SLICES : 1;
-    { const char* e = getenv("B2R_SLICES"); if (e && atoi(e) >= 1 && atoi(e) <= b2r_config::MAX_SLICES && n >= 16384) n_slices = atoi(e); }   // testing hook
-    const bool trace = getenv("B2R_TRACE_HOST") != nullptr;               // timing aid: where the copies sit on the time line
-    cudaEvent_t tev[4] = {};
-    if (trace) for (auto& e : tev) CUDA_TRY(cudaEventCreate(&e));
-    if (trace) CUDA_TRY(cudaEventRecord(tev[0], st));
-    CUDA_TRY(cudaEventRecord(c->ev_fork, st));                           // accumulate uploads / earlier work on the compute stream
-    CUDA_TRY(cudaStreamWaitEvent(c->in_stream, c->ev_fork, 0));
-    CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_fork, 0));
-    if (n) CUDA_TRY(cudaMemcpyAsync(c->ws_offsets.p, h_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->in_stream));
-    std::vector<WalkParams> slice_params(n_slices);
-    std::vector<uint64_t> slice_lo(n_slices);
-    for (int i = 0; i < n_slices; i++) {
-        const uint64_t lo = n * (uint64_t)i / n_slices, hi = n * (uint64_t)(i + 1) / n_slices, ni = hi - lo;
-        slice_lo[i] = lo;
-        const uint64_t b0 = n ? h_offsets[lo] : 0, b1 = n ? h_offsets[hi] : 0;
-        if (b1 < b0) { set_error("offsets must be non-decreasing"); return B2R_ERR_INVALID_ARG; }
-        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_in + (b0 - base), h_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, c->in_stream));
-        CUDA_TRY(cudaEventRecord(c->ev_in[i], c->in_stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[i], 0));
-        b2r_outputs ds = dout;                                           // this slice's rows of every column
-        for (uint32_t d = 0; d < c->n_defs; d++) {
-            const size_t w = c->packed[d].state_width;
-            if (ds.states[d]) ds.states[d] = (unsigned char*)ds.states[d] + lo * rp * w;
-            if (ds.substr_ids[d]) ds.substr_ids[d] += lo * rp;
-            if (ds.start_enable[d]) ds.start_enable[d] += lo * bp;
-            if (ds.end_enable[d]) ds.end_enable[d] += lo * bp;
-        }
-        if (ds.masked_chars) ds.masked_chars += lo * rp;
-        if (ds.masked_substr_ids) ds.masked_substr_ids += lo * rp;
-        if (ds.status) ds.status += lo;
-        if (ds.records) ds.records += lo * (size_t)ho->max_records;
-        if (ds.compact_bytes) ds.compact_bytes += lo * (size_t)ho->compact_pitch;
-        if (i > 0) ds.flags |= B2R_OUT_ACCUMULATE_MULT;                  // the multiplicities of the slices add up
-        rc = match_batch_impl(c, d_bytes, d_offsets + lo, ni, total, &ds, c->max_chars, st);
-        if (rc) return rc;
-        slice_params[i] = c->last;
-        CUDA_TRY(cudaMemcpyAsync(c->h_slices + i, c->scratch, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(c->ev_done[i], st));
-        CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_done[i], 0));
-        if (trace && i == 0) CUDA_TRY(cudaEventRecord(tev[2], c->out_stream));
-        if (trace && i == n_slices - 1) CUDA_TRY(cudaEventRecord(tev[1], c->in_stream));
-        for (const Copy& cp : copies)
-            if (cp.stride && cp.pinned && ni) CUDA_TRY(cudaMemcpyAsync((unsigned char*)cp.host + lo * cp.stride, cb + cp.off + lo * cp.stride, ni * cp.stride, cudaMemcpyDeviceToHost, c->out_stream));
-    }
-    for (const Copy& cp : copies)
-        if (cp.stride && !cp.pinned && n) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, n * cp.stride, cudaMemcpyDeviceToHost, c->out_stream));
-    for (const Copy& cp : copies)
-        if (!cp.stride && cp.bytes) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
-    if (trace) CUDA_TRY(cudaEventRecord(tev[3], c->out_stream));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaStreamSynchronize(c->out_stream));
-    if (trace) {
-        float h2d_end = 0, d2h_begin = 0, d2h_end = 0;
-        cudaEventElapsedTime(&h2d_end, tev[0], tev[1]); cudaEventElapsedTime(&d2h_begin, tev[0], tev[2]); cudaEventElapsedTime(&d2h_end, tev[0], tev[3]);
-        fprintf(stderr, "[b2r] host call, %d slices: last H2D done at %.2f ms, first D2H starts at %.2f ms, last D2H done at %.2f ms\n", n_slices, h2d_end, d2h_begin, d2h_end);
-        for (auto& e : tev) cudaEventDestroy(e);
-    }
-
-    // the batch result: the lowest failing string over all slices (reference: the first panic), overlaps summed
-    b2r_batch_status r;
-    memset(&r, 0, sizeof r);
-    uint64_t n_overlap = 0;
-    for (int i = 0; i < n_slices; i++) n_overlap += c->h_slices[i].n_overlap;
-    for (int i = 0; i < n_slices; i++) {
-        if (c->h_slices[i].first_bad == ~0ull) continue;
-        rc = launch_diagnose(slice_params[i], c->h_slices[i].first_bad, c->d_batch_status, st);
-        if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaMemcpy(&r, c->d_batch_status, sizeof r, cudaMemcpyDeviceToHost));
-        r.string_idx += slice_lo[i];
-        if (r.code == B2R_ERR_INVALID_TRANSITION)
-            set_error("The transition from %u by %u is invalid! (string %llu, position %u, def %u)", r.state, (unsigned)r.byte,
-                      (unsigned long long)r.string_idx, r.pos, (unsigned)r.def);
-        else if (r.code == B2R_ERR_TOO_LONG)
-            set_error("string %llu is longer than max_chars_size-1", (unsigned long long)r.string_idx);
-        break;
-    }
-    r.n_overlap_lo = (uint32_t)n_overlap;
-    if (result) *result = r;
-    return r.code;
-}
-
-int b2r_match_substrs(b2r_config* c, const uint8_t* characters, uint64_t len, const b2r_outputs* h_out, b2r_batch_status* result) {
-    if (!c || !h_out) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
-    const uint64_t offsets[2] = {0, len};
-    return b2r_match_batch_host(c, characters, offsets, 1, h_out, result);
 }
 
 int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2r_outputs* o, void* cuda_stream) {
@@ -664,7 +450,6 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     for (uint32_t d = 0; d < c->n_defs; d++) wide = wide || c->packed[d].state_width == 2;
     c->last_launches = 0;
     CUDA_TRY(cudaMemsetAsync(c->scratch, 0, c->scratch_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(c->scratch, 0xFF, sizeof(unsigned long long), st));  // BatchCounters::first_bad = none
 
     // ---- workspace: chunk offsets (+ the {0, len} pair of the whole string), flag words, summary, tree of transition vectors
     const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (len + LONG_CHUNK - 1) / LONG_CHUNK);
@@ -729,7 +514,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
         if (!pw.def[d].states) pw.def[d].states = ws + off_states[d];
         pw.def[d].init_states = lp.def[d].entry;                          // level 0 of the tree
     }
-    if ((rc = plan_walk(pw, wide, c->force_table_mode, c->force_hist_mode))) return rc;
+    if ((rc = plan_walk(pw, wide, c->opt.force_table_mode, c->opt.force_hist_mode, c->opt.hist_cache_log2))) return rc;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_walk(pw, wide, st, nullptr))) return rc;
     c->last_launches++;
@@ -751,61 +536,50 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     return B2R_OK;
 }
 
-// Host-pointer variant of the long-string path: the string goes up in one copy, the columns come back in one copy each.
-int b2r_match_long_host(b2r_config* c, const uint8_t* h_bytes, uint64_t len, const b2r_outputs* ho, b2r_batch_status* result) {
-    if (!c || !ho || (!h_bytes && len)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
-    if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
-    const uint64_t M = len + 1;
-    int rc = check_outputs(c, ho, false, M);
-    if (rc) return rc;
-    DeviceGuard g(c->device);
-    if (!g.ok) { set_error("cudaSetDevice(%d) failed", c->device); return B2R_ERR_CUDA; }
-    cudaStream_t st = c->host_stream;
-    if ((rc = c->ws_bytes.reserve(align_up(len + 16, 256)))) return rc;
-    const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
-    size_t need = 0;
-    auto slot = [&](size_t bytes) { size_t o = need; need += align_up(bytes, 256); return o; };
-    struct Copy { size_t off; void* host; size_t bytes; };
-    std::vector<Copy> copies;
-    std::vector<size_t> offs;
-    b2r_outputs dout = *ho;
-    auto want = [&](void* host, size_t bytes) -> size_t {
-        if (!host) { offs.push_back(0); return 0; }
-        const size_t o = slot(bytes);
-        copies.push_back({o, host, bytes});
-        offs.push_back(o);
-        return o;
-    };
-    // first pass: sizes; second pass (after the reserve): device pointers
-    for (uint32_t d = 0; d < c->n_defs; d++) {
-        want(ho->states[d], rp * c->packed[d].state_width); want(ho->substr_ids[d], rp); want(ho->start_enable[d], bp); want(ho->end_enable[d], bp);
-        want(ho->mult[d], c->packed[d].rows.size() * 8); want(ho->endpoint_mult[d], c->packed[d].erows.size() * 16);
-    }
-    want(ho->masked_chars, rp); want(ho->masked_substr_ids, rp); want(ho->status, sizeof(b2r_string_status));
-    want(ho->records, (size_t)ho->max_records * sizeof(b2r_substr_record)); want(ho->compact_bytes, (size_t)ho->compact_pitch);
-    if ((rc = c->ws_cols.reserve(need + 256))) return rc;
-    unsigned char* cb = (unsigned char*)c->ws_cols.p;
-    size_t k = 0;
-    auto dev = [&](void* host) -> void* { const size_t o = offs[k++]; return host ? cb + o : nullptr; };
-    for (uint32_t d = 0; d < c->n_defs; d++) {
-        dout.states[d] = dev(ho->states[d]); dout.substr_ids[d] = (uint8_t*)dev(ho->substr_ids[d]);
-        dout.start_enable[d] = (uint8_t*)dev(ho->start_enable[d]); dout.end_enable[d] = (uint8_t*)dev(ho->end_enable[d]);
-        dout.mult[d] = (uint64_t*)dev(ho->mult[d]); dout.endpoint_mult[d] = (uint64_t*)dev(ho->endpoint_mult[d]);
-        if (ho->flags & B2R_OUT_ACCUMULATE_MULT) {
-            if (ho->mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.mult[d], ho->mult[d], c->packed[d].rows.size() * 8, cudaMemcpyHostToDevice, st));
-            if (ho->endpoint_mult[d]) CUDA_TRY(cudaMemcpyAsync(dout.endpoint_mult[d], ho->endpoint_mult[d], c->packed[d].erows.size() * 16, cudaMemcpyHostToDevice, st));
-        }
-    }
-    dout.masked_chars = (uint8_t*)dev(ho->masked_chars); dout.masked_substr_ids = (uint8_t*)dev(ho->masked_substr_ids);
-    dout.status = (b2r_string_status*)dev(ho->status); dout.records = (b2r_substr_record*)dev(ho->records);
-    dout.compact_bytes = (uint8_t*)dev(ho->compact_bytes);
-    if (len) CUDA_TRY(cudaMemcpyAsync(c->ws_bytes.p, h_bytes, len, cudaMemcpyHostToDevice, st));
-    if ((rc = b2r_match_long(c, (const uint8_t*)c->ws_bytes.p, len, &dout, st))) return rc;
-    for (const Copy& cp : copies) CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, cp.bytes, cudaMemcpyDeviceToHost, st));
-    return b2r_batch_result(c, st, result);
+uint32_t b2r_last_launch_count(const b2r_config* c) { return c ? c->last_launches : 0; }
+
+// testing / tuning hooks (the same knobs the B2R_* environment variables set when a handle is created)
+int b2r_config_set_option(b2r_config* c, const char* name, const char* value) {
+    if (!c || !name || !value) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    auto& o = c->opt;
+    const int v = atoi(value);
+    if (!strcmp(name, "table_mode")) o.force_table_mode = parse_table_mode(value);
+    else if (!strcmp(name, "hist_mode")) o.force_hist_mode = parse_hist_mode(value);
+    else if (!strcmp(name, "debug")) o.debug = (uint32_t)v;
+    else if (!strcmp(name, "spread_fill")) o.spread_fill = v ? 1u : 0u;
+    else if (!strcmp(name, "fuse")) o.fuse = v ? 1u : 0u;
+    else if (!strcmp(name, "slices")) o.slices = v;
+    else if (!strcmp(name, "trace_host")) o.trace_host = v != 0;
+    else if (!strcmp(name, "hist_cache_log2")) o.hist_cache_log2 = v;
+    else if (!strcmp(name, "host_threads")) { o.host_threads = v; c->pool.reset(); }
+    else if (!strcmp(name, "small_path")) o.small_path = v;
+    else if (!strcmp(name, "sparse_cap")) o.sparse_cap = v;
+    else { set_error("unknown option '%s'", name); return B2R_ERR_INVALID_ARG; }
+    if (c->multi) return multi_set_option(c->multi, name, value);
+    return B2R_OK;
 }
 
-uint32_t b2r_last_launch_count(const b2r_config* c) { return c ? c->last_launches : 0; }
+// ---- page-locked host memory for the callers of the host-pointer entry points ---------------------------------------------
+int b2r_host_alloc(size_t bytes, void** out) {
+    if (!out) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return B2R_OK;
+}
+int b2r_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return B2R_OK;
+}
+int b2r_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return B2R_OK;
+}
+int b2r_host_unregister(void* p) {
+    if (!p) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    CUDA_TRY(cudaHostUnregister(p));
+    return B2R_OK;
+}
 int b2r_config_set_timing(b2r_config* c, int enable) { if (!c) return B2R_ERR_INVALID_ARG; c->timing = enable != 0; return B2R_OK; }
 int b2r_last_kernel_ms(b2r_config* c, float* walk_ms, float* total_ms) {
     if (!c || !c->timing || c->device < 0) { set_error("timing is not enabled on this handle"); return B2R_ERR_INVALID_ARG; }

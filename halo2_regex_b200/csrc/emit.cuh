@@ -41,7 +41,7 @@ static __device__ __noinline__ b2r_batch_status diagnose_string(const WalkParams
     b2r_batch_status r = {};
     r.string_idx = j;
     const uint64_t off = p.offsets[j], end = p.offsets[j + 1];
-    if (end < off || end - off > (uint64_t)(p.max_chars - 1)) {
+    if (end < off || end - off > (uint64_t)(p.max_chars - 1) || end > p.total_bytes) {
         r.code = B2R_ERR_TOO_LONG; r.pos = NO_POS;
         return r;
     }
@@ -62,7 +62,7 @@ static __device__ __noinline__ b2r_batch_status diagnose_string(const WalkParams
 
 // the reference panics (src/lib.rs:817) / the string does not fit: mark the string, remember the lowest failing index
 static __device__ __noinline__ void kill_string(const WalkParams& p, uint64_t idx) {
-    atomicMin(&p.counters->first_bad, (unsigned long long)idx);
+    atomicMax(&p.counters->first_bad_inv, ~(unsigned long long)idx);
     if (p.status) {
         const b2r_batch_status r = diagnose_string(p, idx);
         b2r_string_status st = {};
@@ -543,7 +543,7 @@ struct TileEmitter {
         const bool valid = jl < N;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[jl]; end = p.offsets[jl + 1]; }
-        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // len must be <= M-1
+        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1) || end > p.total_bytes);   // len must be <= M-1
         const bool live = valid && !too_long;
         const uint32_t Ll = live ? (uint32_t)(end - off) : 0u;
         uint32_t fw0 = 0, fw1 = 0;

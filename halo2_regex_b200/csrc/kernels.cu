@@ -15,6 +15,7 @@ namespace b2r {
 __global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nth = gridDim.x * blockDim.x;
+    if (p.counters_copy && tid == 0) *p.counters_copy = *p.counters;
     for (uint32_t d = 0; d < p.n_defs; d++) {
         const auto& f = p.def[d];
         if (f.mult) {
@@ -59,7 +60,7 @@ static constexpr int MIN_WARPS_REPL = 12;  // below this the replicated tables a
 
 // Picks where the walk tables and the multiplicity bins live.  Preference: replicated tables + shared bins with as many
 // warps as possible; then a single copy of the tables; then global tables.  Bins go to shared memory whenever they fit.
-int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode) {
+int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode, int hist_cache_log2) {
     int n_sm = 0, max_smem = 0;
     int rc = device_limits(&n_sm, &max_smem);
     if (rc) return rc;
@@ -82,8 +83,7 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     };
     // HIST_GLOBAL: the largest bin cache (4096 .. 256 slots per def) that leaves room for the warps
     auto fits = [&](uint32_t tm, uint32_t hm, int warps) {
-        uint32_t top = 12;
-        if (const char* e = getenv("B2R_HIST_CACHE_LOG2")) { const int v = atoi(e); if (v >= 8 && v <= 14) top = (uint32_t)v; }   // tuning hook
+        const uint32_t top = (hist_cache_log2 >= 8 && hist_cache_log2 <= 14) ? (uint32_t)hist_cache_log2 : 12u;   // tuning hook (B2R_HIST_CACHE_LOG2)
         for (p.hist_cache_log2 = top; p.hist_cache_log2 >= 8; p.hist_cache_log2--)
             if (fits_k(tm, hm, warps)) return true;
         p.hist_cache_log2 = 8;
@@ -93,9 +93,9 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     // 32-bit entries; global tables.  A placement is taken when at least `need` warps fit next to it.
     // (single copy: the 16-bit entries win at every size measured — two entries per bank word halve the conflicts and
     //  the footprint: 3-def set 28.9 % -> 31.9 % of HBM peak, 2-def 40.1 -> 43.3, 1023-state DFA 2.2x)
-    const uint32_t P32 = TABLE_PLAIN16, P16 = TABLE_PLAIN;
-    const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P32, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P32, HIST_GLOBAL},
-                                 {P16, HIST_SMEM}, {P16, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
+    const uint32_t P16 = TABLE_PLAIN16, P32 = TABLE_PLAIN;
+    const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P16, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P16, HIST_GLOBAL},
+                                 {P32, HIST_SMEM}, {P32, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
     for (const auto& o : order) {
         if (force_table_mode >= 0 && (uint32_t)force_table_mode != o[0]) continue;   // testing hooks: honoured when they fit
         if (force_hist_mode >= 0 && (uint32_t)force_hist_mode != o[1]) continue;

@@ -36,14 +36,16 @@ struct DefDev {
     uint8_t* end_enable;
 };
 
-struct BatchCounters {               // zeroed (first_bad = ~0) before every batch
-    unsigned long long first_bad;    // lowest string index with an invalid transition / too long
+struct BatchCounters {               // zeroed before every batch (one memset node)
+    unsigned long long first_bad_inv; // ~(lowest string index with an invalid transition / too long), kept with atomicMax; 0 = none
     unsigned long long n_overlap;
     unsigned long long pad_rows;     // sum over strings of (M - len): multiplicity of table row 0
     unsigned long long n_ok_strings; // strings that were processed to the end
     unsigned long long tile_counter; // next tile of 32 strings to hand out (dynamic scheduling of the persistent walk CTAs)
     unsigned long long emit_tile_counter;   // the same for emit_kernel
     unsigned long long reserved[2];
+    __host__ __device__ bool any_bad() const { return first_bad_inv != 0; }
+    __host__ __device__ unsigned long long first_bad() const { return ~first_bad_inv; }
 };
 
 struct WalkParams {
@@ -93,6 +95,7 @@ struct FinalizeParams {
     uint32_t accumulate;
     uint64_t n_rows_total;           // N*M, for the endpoint row-0 counts
     const BatchCounters* counters;
+    BatchCounters* counters_copy;    // optional: a copy of the batch counters next to the outputs (small-batch host path: one D2H copy)
     struct {
         const unsigned long long* hist;
         const uint32_t* row_bin;     // [T]
@@ -113,7 +116,7 @@ struct LaunchInfo {
 // host-callable launchers (kernels.cu / walk_inst.cu)
 // chooses table_mode / hist_mode for this device (force_* >= 0: preferred placement, testing hook); 0 or an error
 int device_limits(int* n_sm, int* max_smem);   // SM count and opt-in shared memory per block of the current device
-int plan_walk(WalkParams& p, bool wide_states, int force_table_mode, int force_hist_mode);
+int plan_walk(WalkParams& p, bool wide_states, int force_table_mode, int force_hist_mode, int hist_cache_log2);
 int launch_walk(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);
 int launch_emit(const WalkParams& p, bool wide_states, void* stream, LaunchInfo* chosen);
 int launch_finalize(const FinalizeParams& p, void* stream);

@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         const bool valid = idx < p.n_strings;
         uint64_t off = 0, end = 0;
         if (valid) { off = p.offsets[idx]; end = p.offsets[idx + 1]; }
-        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1));   // emit reports it; walk nothing
+        // emit reports it; walk nothing.  Offsets that leave the byte buffer are treated the same way
+        // (nothing outside [0, total_bytes) is ever read)
+        const bool too_long = valid && (end < off || end - off > (uint64_t)(M - 1) || end > p.total_bytes);
         if (too_long) end = off;
         const uint32_t L = (uint32_t)(end - off);
         const uint32_t rows_here = (p.n_strings - tile_base < 32) ? (uint32_t)(p.n_strings - tile_base) : 32u;

@@ -153,11 +153,14 @@ class RegexVerifyConfig:
     """reference src/lib.rs:97-113.  `configure` takes the two parameters that matter for witness generation
     (`max_chars_size`, `regex_defs`, src/lib.rs:126-131); `meta` / `gate` belong to the halo2 side and are ignored."""
 
-    def __init__(self, max_chars_size, regex_defs, device=None):
+    def __init__(self, max_chars_size, regex_defs, device=None, devices=None):
         self.max_chars_size = int(max_chars_size)
         self.regex_defs = list(regex_defs)
         for rd in self.regex_defs:
             assert isinstance(rd, RegexDefs)
+        self.devices = [int(x) for x in devices] if devices is not None else None
+        if self.devices is not None:
+            device = -1           # multi-device handle (b2r_config_new_multi): one process, several GPUs
         if device is None:
             try:
                 import torch
@@ -171,7 +174,11 @@ class RegexVerifyConfig:
         subs = (C.POINTER(C.c_void_p) * D)(*[C.cast(a, C.POINTER(C.c_void_p)) for a in sub_arrays])
         ns = (C.c_uint32 * D)(*[len(rd.substrs) for rd in self.regex_defs])
         h = C.c_void_p()
-        rc = lib.b2r_config_new(allstr, subs, ns, D, self.max_chars_size, self.device, C.byref(h))
+        if self.devices is not None:
+            ids = (C.c_int * len(self.devices))(*self.devices)
+            rc = lib.b2r_config_new_multi(allstr, subs, ns, D, self.max_chars_size, ids, len(self.devices), C.byref(h))
+        else:
+            rc = lib.b2r_config_new(allstr, subs, ns, D, self.max_chars_size, self.device, C.byref(h))
         if rc != 0:
             raise RuntimeError(f"b2r_config_new failed ({rc}): {last_error()}")
         self._h = h
@@ -189,8 +196,18 @@ class RegexVerifyConfig:
             lib.b2r_config_free(h)
 
     @classmethod
-    def configure(cls, max_chars_size, regex_defs, meta=None, gate=None, device=None):
-        return cls(max_chars_size, regex_defs, device=device)
+    def configure(cls, max_chars_size, regex_defs, meta=None, gate=None, device=None, devices=None):
+        return cls(max_chars_size, regex_defs, device=device, devices=devices)
+
+    def set_option(self, name, value):
+        """Testing / tuning knobs of the handle (b2r_config_set_option): "table_mode", "hist_mode", "fuse", "slices", ..."""
+        _raise(lib.b2r_config_set_option(self._h, str(name).encode(), str(value).encode()))
+
+    def last_host_bytes(self):
+        """(host->device, device->host) bytes the last host-pointer call moved over PCIe."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _raise(lib.b2r_last_host_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ---- RegexVerifyConfig::load → RegexTableConfig::load (src/lib.rs:779-785, src/table.rs:61-198) -----------------
     def table_rows(self, d):
@@ -211,8 +228,11 @@ class RegexVerifyConfig:
     def new_host_outputs(self, n, **kw):
         return HostOutputs(n, self.max_chars_size, self.state_widths, self.table_num_rows, self.endpoint_num_rows, **kw)
 
-    def match_batch_host(self, data, offsets, out=None, flags=0, check=True, **kw):
-        """Host buffers in, host buffers out (H2D, kernels, D2H inside): the call a drop-in shim makes."""
+    def match_batch_host(self, data, offsets, out=None, flags=0, check=True, sparse=False, **kw):
+        """Host buffers in, host buffers out (H2D, kernels, D2H inside): the call a drop-in shim makes.
+        sparse=True: B2R_OUT_SPARSE_D2H — the zero-dominated columns cross PCIe compacted and are expanded by host threads."""
+        if sparse:
+            flags |= _abi.B2R_OUT_SPARSE_D2H
         data = np.ascontiguousarray(data, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1

@@ -36,7 +36,8 @@ extern "C" {
 #define B2R_ERR_INVALID_ARG (-3)
 #define B2R_ERR_CUDA (-4)               /* CUDA runtime failure / no usable device */
 #define B2R_ERR_INVALID_TRANSITION (-5) /* reference: panic!("The transition from {} by {} is invalid!") src/lib.rs:817 */
-#define B2R_ERR_TOO_LONG (-6)           /* a string has len > max_chars_size-1 (final-state row would be lost, src/lib.rs:404-418) */
+#define B2R_ERR_TOO_LONG (-6)           /* a string has len > max_chars_size-1 (final-state row would be lost, src/lib.rs:404-418),
+                                           or its offsets leave [0, total_bytes] */
 #define B2R_ERR_UNSUPPORTED (-7)        /* definition outside what the packed tables can hold (see b2r_config_new) */
 #define B2R_ERR_ALIGNMENT (-8)          /* an output pointer / pitch violates the documented alignment */
 
@@ -110,6 +111,28 @@ uint32_t b2r_config_num_byte_classes(const b2r_config*, uint32_t d); /* incl. th
 uint64_t b2r_config_recommended_row_pitch(const b2r_config*);
 uint64_t b2r_config_recommended_bitmap_pitch(const b2r_config*);
 
+/* One process, several GPUs (reference call site src/lib.rs:311-318 is one process): the same definitions
+ * bound to `n_devices` CUDA devices.  b2r_match_batch_host on such a handle shards the strings into contiguous ranges balanced
+ * by bytes, runs one host thread + stream set per device, and sums the multiplicity counters with ONE ncclAllReduce (u64 sum)
+ * over NVLink before they are copied back; every other column needs no exchange.  NCCL is resolved at run time
+ * (dlopen "libnccl.so.2"); B2R_ERR_UNSUPPORTED when it cannot be loaded.  Table queries work as on a single-device handle;
+ * the device-pointer entry points need a single-device handle. */
+int b2r_config_new_multi(const b2r_allstr* const* allstr, const b2r_substr* const* const* substrs,
+                         const uint32_t* n_substrs, uint32_t n_defs, uint64_t max_chars_size, const int* device_ids,
+                         uint32_t n_devices, b2r_config** out);
+uint32_t b2r_config_num_devices(const b2r_config*);
+/* testing / tuning knobs of a handle, the same ones the B2R_* environment variables set when it is created
+ * ("table_mode", "hist_mode", "fuse", "slices", "host_threads", "small_path", ...) */
+int b2r_config_set_option(b2r_config*, const char* name, const char* value);
+
+/* Page-locked host memory for the buffers handed to the host-pointer entry points (a copy into pageable memory cannot overlap
+ * with anything): b2r_host_alloc / b2r_host_free own the memory, b2r_host_register / b2r_host_unregister pin memory the caller
+ * already owns (e.g. a Rust Vec). */
+int b2r_host_alloc(size_t bytes, void** out);
+int b2r_host_free(void* p);
+int b2r_host_register(void* p, size_t bytes);
+int b2r_host_unregister(void* p);
+
 /* RegexTableConfig::load row order (src/table.rs:101-122): row 0 = (0,dummy,dummy,0), then state_lookup sorted by
  * line index, each with the first-match substr id.  out4[r] = {char, cur_state, next_state, substr_id}. */
 uint64_t b2r_table_num_rows(const b2r_config*, uint32_t d);
@@ -125,7 +148,7 @@ int b2r_endpoint_rows(const b2r_config*, uint32_t d, uint64_t* out3, uint64_t ca
                                               and/not/select arithmetic is non-boolean there (src/lib.rs:613-642);
                                               masked outputs / records of this string are unspecified */
 #define B2R_ST_INVALID_TRANSITION (1u << 9) /* reference panics (src/lib.rs:817); err_* describe the first one */
-#define B2R_ST_TOO_LONG (1u << 10)         /* len > max_chars_size-1: string skipped, its rows are unspecified */
+#define B2R_ST_TOO_LONG (1u << 10)         /* len > max_chars_size-1 (or offsets outside the byte buffer): string skipped, its rows are unspecified */
 #define B2R_ST_RECORDS_TRUNCATED (1u << 11)
 #define B2R_ST_COMPACT_TRUNCATED (1u << 12)
 
@@ -176,6 +199,12 @@ typedef struct b2r_batch_status {
  *                    [E_d,2E_d) those of the end-endpoint lookup (src/lib.rs:260-284), rows of b2r_endpoint_rows
  * Invariants: sum_r mult[d][r] = N*M; each half of endpoint_mult[d] sums to N*M. */
 #define B2R_OUT_ACCUMULATE_MULT 1u /* add into mult/endpoint_mult instead of overwriting them */
+#define B2R_OUT_SPARSE_D2H 2u      /* host-pointer entry points only: substr_ids, start_enable, end_enable, masked_chars and
+                                      masked_substr_ids are zero almost everywhere; with this flag they cross PCIe as their non-zero
+                                      32-byte sectors (compacted on the device after the kernels wrote the dense columns) and are
+                                      expanded into the caller's dense buffers by host threads inside the call (memset + scatter).
+                                      Same results, about a third of the device-to-host bytes.  A column slice that is not sparse
+                                      after all is copied densely. */
 
 typedef struct b2r_outputs {
     uint64_t row_pitch;    /* >= M */
@@ -232,6 +261,8 @@ int b2r_match_long_host(b2r_config* cfg, const uint8_t* h_bytes, uint64_t len, c
 
 /* kernel launches enqueued by the last b2r_match_* call on this handle (for benchmark accounting) */
 uint32_t b2r_last_launch_count(const b2r_config*);
+/* bytes the last host-pointer call moved over PCIe in each direction */
+int b2r_last_host_bytes(const b2r_config*, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* name + device time (ms, CUDA events on the launching stream) of the dominant kernel of the last call;
  * valid after b2r_batch_result().  Enabled by b2r_config_set_timing(cfg,1). */
 int b2r_config_set_timing(b2r_config*, int enable);

@@ -9,6 +9,7 @@
 //   AssignedRegexResult                                          reference src/lib.rs:79-93 (integer values, not cells)
 // Where the reference panics, these throw (std::runtime_error with the reference's panic text for an invalid transition).
 #pragma once
+#include <array>
 #include <cstdint>
 #include <memory>
 #include <set>
@@ -154,6 +155,63 @@ public:
         detail::check(b2r_config_new(allstr.data(), sub_ptrs.data(), n_subs.data(), (uint32_t)regex_defs.size(), max_chars_size, device, &h));
         c.h_ = std::shared_ptr<b2r_config>(h, b2r_config_free);
         return c;
+    }
+    // The same chip bound to several GPUs of one process (b2r_config_new_multi): match_batch shards the strings over them.
+    static RegexVerifyConfig configure_multi(size_t max_chars_size, const std::vector<RegexDefs>& regex_defs, const std::vector<int>& devices) {
+        RegexVerifyConfig c;
+        c.max_chars_size = max_chars_size;
+        c.regex_defs = regex_defs;
+        std::vector<const b2r_allstr*> allstr;
+        std::vector<std::vector<const b2r_substr*>> subs(regex_defs.size());
+        std::vector<const b2r_substr* const*> sub_ptrs;
+        std::vector<uint32_t> n_subs;
+        for (size_t d = 0; d < regex_defs.size(); d++) {
+            allstr.push_back(regex_defs[d].allstr.handle());
+            for (const auto& s : regex_defs[d].substrs) subs[d].push_back(s.handle());
+            sub_ptrs.push_back(subs[d].data());
+            n_subs.push_back((uint32_t)subs[d].size());
+        }
+        b2r_config* h = nullptr;
+        detail::check(b2r_config_new_multi(allstr.data(), sub_ptrs.data(), n_subs.data(), (uint32_t)regex_defs.size(), max_chars_size, devices.data(),
+                                           (uint32_t)devices.size(), &h));
+        c.h_ = std::shared_ptr<b2r_config>(h, b2r_config_free);
+        return c;
+    }
+
+    // Every witness column of a batch of strings (the bulk form of match_substrs): row-major, `row_pitch` / `bitmap_pitch` bytes
+    // per string, plus the lookup multiplicities per table row (b2r.h).
+    struct BatchWitness {
+        size_t n = 0, row_pitch = 0, bitmap_pitch = 0;
+        std::vector<std::vector<uint8_t>> states, substr_ids, start_enable, end_enable;   // per def (states: state_width bytes per row)
+        std::vector<uint8_t> masked_chars, masked_substr_ids;
+        std::vector<b2r_string_status> status;
+        std::vector<std::vector<uint64_t>> mult, endpoint_mult;
+    };
+    BatchWitness match_batch(const std::vector<std::vector<uint8_t>>& strings, bool sparse_d2h = false) const {
+        const size_t M = max_chars_size, D = regex_defs.size(), n = strings.size();
+        BatchWitness w;
+        w.n = n; w.row_pitch = (M + 31) & ~size_t(31); w.bitmap_pitch = ((M + 7) / 8 + 31) & ~size_t(31);
+        std::vector<uint8_t> bytes;
+        std::vector<uint64_t> offsets(n + 1, 0);
+        for (size_t j = 0; j < n; j++) { bytes.insert(bytes.end(), strings[j].begin(), strings[j].end()); offsets[j + 1] = bytes.size(); }
+        b2r_outputs out{};
+        out.row_pitch = w.row_pitch; out.bitmap_pitch = w.bitmap_pitch; out.flags = sparse_d2h ? B2R_OUT_SPARSE_D2H : 0;
+        w.states.resize(D); w.substr_ids.resize(D); w.start_enable.resize(D); w.end_enable.resize(D); w.mult.resize(D); w.endpoint_mult.resize(D);
+        for (size_t d = 0; d < D; d++) {
+            w.states[d].resize(n * w.row_pitch * b2r_config_state_width(h_.get(), (uint32_t)d)); w.substr_ids[d].resize(n * w.row_pitch);
+            w.start_enable[d].resize(n * w.bitmap_pitch); w.end_enable[d].resize(n * w.bitmap_pitch);
+            w.mult[d].resize(b2r_table_num_rows(h_.get(), (uint32_t)d)); w.endpoint_mult[d].resize(2 * b2r_endpoint_num_rows(h_.get(), (uint32_t)d));
+            out.states[d] = w.states[d].data(); out.substr_ids[d] = w.substr_ids[d].data();
+            out.start_enable[d] = w.start_enable[d].data(); out.end_enable[d] = w.end_enable[d].data();
+            out.mult[d] = w.mult[d].data(); out.endpoint_mult[d] = w.endpoint_mult[d].data();
+        }
+        w.masked_chars.resize(n * w.row_pitch); w.masked_substr_ids.resize(n * w.row_pitch); w.status.resize(n);
+        out.masked_chars = w.masked_chars.data(); out.masked_substr_ids = w.masked_substr_ids.data(); out.status = w.status.data();
+        b2r_batch_status res{};
+        const int rc = b2r_match_batch_host(h_.get(), bytes.data(), offsets.data(), n, &out, &res);
+        if (rc == B2R_ERR_INVALID_TRANSITION) throw InvalidTransition(res);
+        detail::check(rc);
+        return w;
     }
 
     // match_substrs (src/lib.rs:311-315): one &[u8] in, the assigned values out
