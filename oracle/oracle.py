@@ -13,8 +13,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
-from halo2_regex_b200 import _abi  # noqa: E402  (struct layouts only)
-from halo2_regex_b200.buffers import HostOutputs  # noqa: E402
+from b2r_layout import abi as _abi  # noqa: E402  (struct layouts only; neutral package, loads no native library)
+from b2r_layout.buffers import HostOutputs  # noqa: E402
 
 _LIB = None
 
