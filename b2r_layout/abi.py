@@ -21,6 +21,7 @@ B2R_ST_COMPACT_TRUNCATED = 1 << 12
 
 B2R_OUT_ACCUMULATE_MULT = 1
 B2R_OUT_SPARSE_D2H = 2
+B2R_OUT_SPARSE_REUSE = 4
 
 
 def B2R_ST_ACCEPTED(d):

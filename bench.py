@@ -419,22 +419,24 @@ def e2e_leg(ctx, H, cfg, d_bytes, n, L, steps):
         ok = 0
     if not ctx.all_true(ok):
         return None
-    for mode, sparse in (("dense", False), ("sparse", True)):
+    for mode, sparse, reuse in (("dense", False, False), ("sparse", True, False), ("sparse_reuse", True, True)):
         ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            cfg.match_batch_host(h_in, h_offs, out=hout, sparse=sparse)
+            cfg.match_batch_host(h_in, h_offs, out=hout, sparse=sparse, reuse=reuse)
         dt = ctx.max_over_ranks(time.perf_counter() - t0)
         h2d, d2h = cfg.last_host_bytes()
         assert int(hout.mult[0].sum()) == n * M
         res[mode] = {"value": world * in_bytes * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
                      "ms_per_step": dt / steps * 1e3}
-    # the two modes must hand the caller the same bytes: compare a checksum of every column of the last sparse call with a dense one
+    # the modes must hand the caller the same bytes: a sampled checksum of every column of the last sparse call against a dense one
     sums_sparse = [int(np.add.reduce(a.view(np.uint8).reshape(-1)[::1 << 6].astype(np.uint64))) for a in hout.all_arrays()]
     cfg.match_batch_host(h_in, h_offs, out=hout)
     sums_dense = [int(np.add.reduce(a.view(np.uint8).reshape(-1)[::1 << 6].astype(np.uint64))) for a in hout.all_arrays()]
-    e2e = dict(res["sparse"])
-    e2e["api"] = "b2r_match_batch_host (include/b2r.h), flags = B2R_OUT_SPARSE_D2H, pinned host buffers from b2r_host_alloc; every column lands dense in the caller's buffers"
+    e2e = dict(res["sparse_reuse"])
+    e2e["api"] = ("b2r_match_batch_host (include/b2r.h), flags = B2R_OUT_SPARSE_D2H | B2R_OUT_SPARSE_REUSE, pinned host buffers from b2r_host_alloc reused batch "
+                  "after batch; every column lands dense in the caller's buffers")
+    e2e["sparse_fresh_buffers"] = res["sparse"]
     e2e["dense_d2h"] = res["dense"]
     e2e["sparse_equals_dense_sampled_checksum"] = ctx.all_true(sums_sparse == sums_dense)
     alloc.free()

@@ -350,8 +350,7 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         CUDA_TRY(cudaStreamCreateWithFlags(&c->pay_stream, cudaStreamNonBlocking));
         for (auto& e : c->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto& e : c->ev_pay) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CUDA_TRY(cudaMallocHost((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES));
+        CUDA_TRY(cudaHostAlloc((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES, cudaHostAllocPortable | cudaHostAllocMapped));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     }
@@ -369,14 +368,13 @@ void b2r_config_free(b2r_config* c) {
         c->ws_fmask.release(); c->ws_long.release();
         for (auto& b : c->ws_states) b.release();
         c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release(); c->ws_sparse.release();
-        c->pin_sparse.release(); c->pin_small.release();
+        c->pin_sparse[0].release(); c->pin_sparse[1].release(); c->pin_small.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         if (c->in_stream) cudaStreamDestroy(c->in_stream);
         if (c->out_stream) cudaStreamDestroy(c->out_stream);
         if (c->pay_stream) cudaStreamDestroy(c->pay_stream);
         for (auto& e : c->ev_in) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_done) if (e) cudaEventDestroy(e);
-        for (auto& e : c->ev_pay) if (e) cudaEventDestroy(e);
         if (c->h_slices) cudaFreeHost(c->h_slices);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);

@@ -51,7 +51,7 @@ struct PinBuf {                       // page-locked host allocation that only g
         if (n <= cap) return B2R_OK;
         if (p) CUDA_TRY(cudaFreeHost(p));
         p = nullptr; cap = 0;
-        CUDA_TRY(cudaHostAlloc(&p, n, cudaHostAllocPortable));
+        CUDA_TRY(cudaHostAlloc(&p, n, cudaHostAllocPortable | cudaHostAllocMapped));   // unified addressing: kernels may write it directly
         cap = n;
         return B2R_OK;
     }
@@ -100,6 +100,17 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 struct MultiState;                    // host.cu: the children of a multi-device handle and their NCCL communicators
 
+// What the last sparse-D2H call scattered into which host buffers (B2R_OUT_SPARSE_REUSE: the next call on the same buffers clears
+// exactly those sectors instead of zeroing the whole columns).  The sector index lists themselves stay in the pinned arena.
+struct SparseMemo {
+    bool valid = false;
+    uint64_t n = 0, rp = 0, bp = 0;
+    int n_slices = 0, sparse_cap = 0, arena = 0;   // arena: which of the two pinned arenas holds the index lists
+    std::vector<const void*> hosts;   // caller's buffer of every sparse column
+    std::vector<uint32_t> cnt;        // [slice][column] sectors scattered
+    std::vector<char> dense;          // [slice][column] 1: that column slice was copied densely
+};
+
 }  // namespace b2r
 
 struct b2r_config {
@@ -137,17 +148,18 @@ struct b2r_config {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before walk, after walk, after emit, after finalize
     // staging for the host-pointer entry points
     b2r::DevBuf ws_bytes, ws_offsets, ws_cols, ws_sparse;
-    b2r::PinBuf pin_sparse, pin_small;
+    b2r::PinBuf pin_sparse[2], pin_small;
     cudaStream_t host_stream = nullptr;
     cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host entry point: H2D / D2H copies overlapping the kernels
     cudaStream_t pay_stream = nullptr;                        // sparse D2H mode: the compacted sectors of a slice
     b2r::BatchCounters* counters_copy = nullptr;              // small-batch path: finalize_kernel leaves a copy of the batch counters here
-    static constexpr int MAX_SLICES = 8;
-    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {}, ev_pay[MAX_SLICES] = {};
+    static constexpr int MAX_SLICES = 16;
+    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
     b2r::BatchCounters* h_slices = nullptr;    // pinned: the counters of every slice of a host batch
     cudaEvent_t ev_fork = nullptr;
     std::unique_ptr<b2r::HostPool> pool;       // created by the first sparse-mode call
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last host call moved over PCIe
+    b2r::SparseMemo sparse_memo;
     b2r::MultiState* multi = nullptr;          // non-null: a multi-device handle (b2r_config_new_multi); `device` = its first device
 };
 

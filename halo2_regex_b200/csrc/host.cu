@@ -15,6 +15,7 @@
 #include <nccl.h>   // types and prototypes only: the library is dlopen'ed (libb2r.so does not link against NCCL)
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,6 +86,12 @@ __global__ void __launch_bounds__(256) sparsify_kernel(const uint4* __restrict__
     }
 }
 
+// the sector counts of one slice -> pinned host memory (a store over PCIe instead of a copy: the copy engines are busy with the
+// dense columns, and a small copy queued behind them would stall the compute stream)
+__global__ void publish_counts_kernel(const unsigned int* __restrict__ dev_cnt, unsigned int* host_cnt, uint32_t n) {
+    if (threadIdx.x < n) host_cnt[threadIdx.x] = dev_cnt[threadIdx.x];
+}
+
 }  // namespace b2r
 
 namespace {
@@ -103,7 +110,9 @@ unsigned default_host_threads() {
     if (!hw) hw = 4;
     unsigned share = 1;                // ranks of a torchrun job share the host cores
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) share = (unsigned)v; }
-    return std::max(2u, std::min(16u, hw / share));
+    // half the cores, at most 8: more threads take memory bandwidth from the DMA engines (2^20 x 1 KiB strings, 16-core host:
+    // 40.5 ms per call with 4 threads, 35.9 with 8, 36.4 with 12, 39.6 with 16)
+    return std::max(2u, std::min(8u, hw / 2 / share));
 }
 
 struct SparseCol {                     // one zero-dominated column of a host batch
@@ -297,7 +306,7 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
     unsigned char* const d_in = (unsigned char*)c->ws_bytes.p + (base & 15);
     const uint8_t* d_bytes = d_in - base;
     const uint64_t* d_offsets = (const uint64_t*)c->ws_offsets.p;
-    int n_slices = n >= 16384 ? b2r_config::MAX_SLICES : 1;
+    int n_slices = n >= 16384 ? (n >= (1u << 19) ? 16 : 8) : 1;
     if (c->opt.slices >= 1 && c->opt.slices <= b2r_config::MAX_SLICES && n >= 16384) n_slices = c->opt.slices;   // testing hook
     // slice boundaries are multiples of 32 strings: whole tiles per slice, and lo * pitch keeps the 16-byte alignment of every
     // column for any legal pitch (bitmap_pitch is only a multiple of 4)
@@ -310,6 +319,8 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
     struct SliceCol { size_t idx_off, pay_off; uint32_t cap; uint64_t n_sectors, bytes; };
     std::vector<SliceCol> sc(n_sc * n_slices);
     size_t sp_need = 0, cnt_off = 0;
+    bool reuse = false;
+    int arena = 0;
     if (sparse && n_sc) {
         auto sslot = [&](size_t bytes) { sp_need = align_up(sp_need, 256); size_t o = sp_need; sp_need += bytes; return o; };
         cnt_off = sslot(n_sc * n_slices * sizeof(unsigned int));
@@ -320,27 +331,62 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
                 s.bytes = ni * scols[k]->stride;
                 s.n_sectors = (s.bytes + 31) / 32;
                 if (s.n_sectors > 0xFFFFFFFFull) { set_error("sparse D2H: a slice of more than 2^32 sectors"); return B2R_ERR_UNSUPPORTED; }
-                s.cap = (uint32_t)std::min<uint64_t>(s.n_sectors, 4 * ni + 1024);   // a handful of non-zero sectors per string; more -> dense copy
+                s.cap = (uint32_t)std::min<uint64_t>(s.n_sectors, 2 * ni + 1024);   // a sector or two per string and column; more -> dense copy
                 if (c->opt.sparse_cap > 0) s.cap = (uint32_t)std::min<uint64_t>(s.n_sectors, (uint64_t)c->opt.sparse_cap);
                 s.idx_off = sslot((size_t)s.cap * 4);
                 s.pay_off = sslot((size_t)s.cap * 32);
             }
         }
-        if ((rc = c->ws_sparse.reserve(sp_need + 256))) return rc;
-        if ((rc = c->pin_sparse.reserve(sp_need + 256))) return rc;
+        // the compacted sectors are written by the kernel straight into page-locked host memory (stores over PCIe, no copy to size
+        // and issue); two arenas alternate so that the index lists of the previous call survive until they have been used
+        arena = c->sparse_memo.arena ^ 1;
+        if ((rc = c->ws_sparse.reserve(n_sc * n_slices * sizeof(unsigned int) + 256))) return rc;
+        if ((rc = c->pin_sparse[arena].reserve(sp_need + 256))) return rc;
         if (!c->pool) c->pool.reset(new HostPool(c->opt.host_threads > 0 ? (unsigned)c->opt.host_threads : default_host_threads()));
-        CUDA_TRY(cudaMemsetAsync((unsigned char*)c->ws_sparse.p + cnt_off, 0, n_sc * n_slices * sizeof(unsigned int), st));
-        // the zeros of the caller's dense columns are written here, by the host, while the GPU works
-        for (size_t k = 0; k < n_sc; k++) {
-            unsigned char* h = (unsigned char*)scols[k]->host;
-            const size_t bytes = scols[k]->bytes, piece = 4u << 20;
-            for (size_t o = 0; o < bytes; o += piece) c->pool->submit([h, o, bytes, piece] { memset(h + o, 0, std::min(piece, bytes - o)); });
+        CUDA_TRY(cudaMemsetAsync(c->ws_sparse.p, 0, n_sc * n_slices * sizeof(unsigned int), st));
+        // B2R_OUT_SPARSE_REUSE: these are the buffers the previous call filled (same batch geometry, hence the same arena layout):
+        // only the sectors it scattered are non-zero, and their index lists are still in the pinned arena
+        SparseMemo& memo = c->sparse_memo;
+        reuse = (ho->flags & B2R_OUT_SPARSE_REUSE) && memo.valid && memo.n == n && memo.rp == rp && memo.bp == bp && memo.n_slices == n_slices &&
+                memo.sparse_cap == c->opt.sparse_cap && memo.hosts.size() == n_sc && c->pin_sparse[memo.arena].p;
+        for (size_t k = 0; reuse && k < n_sc; k++) reuse = memo.hosts[k] == scols[k]->host;
+        memo.valid = false;                                               // until this call has completed
+        if (reuse) {
+            const uint32_t piece = 1u << 16;
+            for (int i = 0; i < n_slices; i++)
+                for (size_t k = 0; k < n_sc; k++) {
+                    const SliceCol& s = sc[i * n_sc + k];
+                    unsigned char* dst = (unsigned char*)scols[k]->host + cut(i) * scols[k]->stride;
+                    const uint64_t bytes = s.bytes;
+                    if (memo.dense[i * n_sc + k]) { c->pool->submit([dst, bytes] { memset(dst, 0, bytes); }); continue; }
+                    const uint32_t cnt = memo.cnt[i * n_sc + k];
+                    const uint32_t* idx = (const uint32_t*)((unsigned char*)c->pin_sparse[memo.arena].p + s.idx_off);
+                    for (uint32_t e0 = 0; e0 < cnt; e0 += piece)
+                        c->pool->submit([=] {
+                            const uint32_t e1 = std::min(cnt, e0 + piece);
+                            for (uint32_t e = e0; e < e1; e++) {   // one cache miss per sector: keep a dozen in flight
+                                if (e + 12 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 12] * 32, 1, 0);
+                                const uint64_t o = (uint64_t)idx[e] * 32;
+                                memset(dst + o, 0, (size_t)std::min<uint64_t>(32, bytes - o));
+                            }
+                        });
+                }
+        } else {
+            // the zeros of the caller's dense columns are written here, by the host, while the GPU works
+            for (size_t k = 0; k < n_sc; k++) {
+                unsigned char* h = (unsigned char*)scols[k]->host;
+                const size_t bytes = scols[k]->bytes, piece = 4u << 20;
+                for (size_t o = 0; o < bytes; o += piece) c->pool->submit([h, o, bytes, piece] { memset(h + o, 0, std::min(piece, bytes - o)); });
+            }
         }
     }
-    unsigned char* const sp_dev = (unsigned char*)c->ws_sparse.p;
-    unsigned char* const sp_host = (unsigned char*)c->pin_sparse.p;
+    unsigned int* const d_cnt = (unsigned int*)c->ws_sparse.p;
+    unsigned char* const sp_host = (unsigned char*)c->pin_sparse[arena].p;   // unified addressing: the kernels write through the same pointer
 
     const bool trace = c->opt.trace_host;                                 // timing aid: where the copies sit on the time line
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto wall_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
+    double w_enq = 0, w_pay = 0, w_zero = 0, w_scat = 0;
     cudaEvent_t tev[4] = {};
     if (trace) for (auto& e : tev) CUDA_TRY(cudaEventCreate(&e));
     if (trace) CUDA_TRY(cudaEventRecord(tev[0], st));
@@ -374,19 +420,23 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
         if (ds.records) ds.records += lo * (size_t)ho->max_records;
         if (ds.compact_bytes) ds.compact_bytes += lo * (size_t)ho->compact_pitch;
         if (i > 0 || hook) ds.flags |= B2R_OUT_ACCUMULATE_MULT;          // the multiplicities of the slices add up
+        c->counters_copy = c->h_slices + i;                              // finalize_kernel leaves the slice's counters in pinned host memory
         rc = match_batch_impl(c, d_bytes, d_offsets + lo, ni, total, &ds, c->max_chars, st);
+        c->counters_copy = nullptr;
         if (rc) return rc;
         slice_params[i] = c->last;
         if (sparse && ni)
             for (size_t k = 0; k < n_sc; k++) {
                 const SliceCol& s = sc[i * n_sc + k];
                 const unsigned grid = (unsigned)std::min<uint64_t>((s.n_sectors + 255) / 256, (uint64_t)n_sm * 8);
-                sparsify_kernel<<<grid, 256, 0, st>>>((const uint4*)(cb + scols[k]->off + lo * scols[k]->stride), s.n_sectors, (uint32_t*)(sp_dev + s.idx_off),
-                                                      (uint4*)(sp_dev + s.pay_off), s.cap, (unsigned int*)(sp_dev + cnt_off) + i * n_sc + k);
+                sparsify_kernel<<<grid, 256, 0, st>>>((const uint4*)(cb + scols[k]->off + lo * scols[k]->stride), s.n_sectors, (uint32_t*)(sp_host + s.idx_off),
+                                                      (uint4*)(sp_host + s.pay_off), s.cap, d_cnt + i * n_sc + k);
                 CUDA_TRY(cudaGetLastError());
             }
-        if (sparse && n_sc) CUDA_TRY(cudaMemcpyAsync(sp_host + cnt_off + i * n_sc * 4, sp_dev + cnt_off + i * n_sc * 4, n_sc * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(c->h_slices + i, c->scratch, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+        if (sparse && n_sc) {
+            publish_counts_kernel<<<1, 32, 0, st>>>(d_cnt + i * n_sc, (unsigned int*)(sp_host + cnt_off) + i * n_sc, (uint32_t)n_sc);
+            CUDA_TRY(cudaGetLastError());
+        }
         CUDA_TRY(cudaEventRecord(c->ev_done[i], st));
         CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_done[i], 0));
         if (trace && i == 0) CUDA_TRY(cudaEventRecord(tev[2], c->out_stream));
@@ -397,61 +447,64 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
                 d2h += ni * cp.stride;
             }
     }
+    w_enq = wall_ms();
     // multi-device handle: the one exchange of the path, NVLink all-reduce of the multiplicity block
     if (hook && mult_end > mult_begin) {
         const ncclResult_t nr = hook->all_reduce(cb + mult_begin, cb + mult_begin, (mult_end - mult_begin) / 8, ncclUint64, ncclSum, hook->comm, st);
         if (nr != ncclSuccess) { set_error("ncclAllReduce failed: %s", hook->error_string(nr)); return B2R_ERR_CUDA; }
     }
-    // ---- sparse mode: the compacted sectors follow on their own stream, sized by the counts ----------------------------------------
+    // ---- sparse mode: the compacted sectors of slice i are in host memory when ev_done[i] fires; host threads scatter them -----------
     if (sparse && n_sc) {
         const unsigned int* h_cnt = (const unsigned int*)(sp_host + cnt_off);
         std::vector<char> dense(n_sc * n_slices, 0);
-        bool waited = false;
+        w_pay = wall_ms();
+        c->pool->wait();                                                  // the zeros are in place (reused buffers: the old sectors are cleared)
+        w_zero = wall_ms();
+        bool any_dense = false;
         for (int i = 0; i < n_slices; i++) {
             const uint64_t lo = slice_lo[i], ni = cut(i + 1) - lo;
             CUDA_TRY(cudaEventSynchronize(c->ev_done[i]));
-            CUDA_TRY(cudaStreamWaitEvent(c->pay_stream, c->ev_done[i], 0));
+            d2h += n_sc * 4;
             for (size_t k = 0; k < n_sc && ni; k++) {
                 const SliceCol& s = sc[i * n_sc + k];
                 const uint32_t cnt = h_cnt[i * n_sc + k];
-                if (cnt > s.cap) {   // not sparse after all: this column slice crosses densely (after the host zeroing, which it overwrites)
-                    if (!waited) { c->pool->wait(); waited = true; }
-                    dense[i * n_sc + k] = 1;
-                    CUDA_TRY(cudaMemcpyAsync((unsigned char*)scols[k]->host + lo * scols[k]->stride, cb + scols[k]->off + lo * scols[k]->stride, s.bytes, cudaMemcpyDeviceToHost, c->pay_stream));
-                    d2h += s.bytes;
-                } else if (cnt) {
-                    CUDA_TRY(cudaMemcpyAsync(sp_host + s.idx_off, sp_dev + s.idx_off, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->pay_stream));
-                    CUDA_TRY(cudaMemcpyAsync(sp_host + s.pay_off, sp_dev + s.pay_off, (size_t)cnt * 32, cudaMemcpyDeviceToHost, c->pay_stream));
-                    d2h += (size_t)cnt * 36;
-                }
-            }
-            d2h += n_sc * 4;
-            CUDA_TRY(cudaEventRecord(c->ev_pay[i], c->pay_stream));
-        }
-        c->pool->wait();                                                  // the zeros are in place
-        for (int i = 0; i < n_slices; i++) {
-            const uint64_t lo = slice_lo[i];
-            CUDA_TRY(cudaEventSynchronize(c->ev_pay[i]));
-            for (size_t k = 0; k < n_sc; k++) {
-                const SliceCol& s = sc[i * n_sc + k];
-                const uint32_t cnt = h_cnt[i * n_sc + k];
-                if (dense[i * n_sc + k] || !cnt) continue;
                 unsigned char* dst = (unsigned char*)scols[k]->host + lo * scols[k]->stride;
+                if (cnt > s.cap) {   // not sparse after all: this column slice crosses densely
+                    dense[i * n_sc + k] = 1;
+                    if (!any_dense) CUDA_TRY(cudaStreamWaitEvent(c->pay_stream, c->ev_done[i], 0));
+                    any_dense = true;
+                    CUDA_TRY(cudaMemcpyAsync(dst, cb + scols[k]->off + lo * scols[k]->stride, s.bytes, cudaMemcpyDeviceToHost, c->pay_stream));
+                    d2h += s.bytes;
+                    continue;
+                }
+                if (!cnt) continue;
+                d2h += (size_t)cnt * 36;
                 const uint32_t* idx = (const uint32_t*)(sp_host + s.idx_off);
                 const unsigned char* pay = sp_host + s.pay_off;
                 const uint64_t bytes = s.bytes;
-                const uint32_t piece = 1u << 16;
+                const uint32_t piece = 1u << 15;
                 for (uint32_t e0 = 0; e0 < cnt; e0 += piece)
                     c->pool->submit([=] {
                         const uint32_t e1 = std::min(cnt, e0 + piece);
                         for (uint32_t e = e0; e < e1; e++) {
+                            if (e + 12 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 12] * 32, 1, 0);
                             const uint64_t o = (uint64_t)idx[e] * 32;
                             memcpy(dst + o, pay + (size_t)e * 32, (size_t)std::min<uint64_t>(32, bytes - o));
                         }
                     });
             }
         }
+        if (any_dense) CUDA_TRY(cudaStreamSynchronize(c->pay_stream));
         c->pool->wait();
+        w_scat = wall_ms();
+        SparseMemo& memo = c->sparse_memo;                                // what the next B2R_OUT_SPARSE_REUSE call has to clear
+        memo.n = n; memo.rp = rp; memo.bp = bp; memo.n_slices = n_slices; memo.sparse_cap = c->opt.sparse_cap;
+        memo.hosts.clear();
+        for (size_t k = 0; k < n_sc; k++) memo.hosts.push_back(scols[k]->host);
+        memo.cnt.assign(h_cnt, h_cnt + n_sc * n_slices);
+        memo.dense = dense;
+        memo.arena = arena;
+        memo.valid = true;
     }
     for (const Copy& cp : copies)
         if (cp.stride && !cp.pinned && !cp.sparse && n) { CUDA_TRY(cudaMemcpyAsync(cp.host, cb + cp.off, n * cp.stride, cudaMemcpyDeviceToHost, c->out_stream)); d2h += n * cp.stride; }
@@ -464,7 +517,9 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
         float h2d_end = 0, d2h_begin = 0, d2h_end = 0;
         cudaEventElapsedTime(&h2d_end, tev[0], tev[1]); cudaEventElapsedTime(&d2h_begin, tev[0], tev[2]); cudaEventElapsedTime(&d2h_end, tev[0], tev[3]);
         fprintf(stderr, "[b2r] host call, %d slices%s: last H2D done at %.2f ms, first D2H starts at %.2f ms, last D2H done at %.2f ms\n", n_slices,
-                sparse ? " (sparse D2H)" : "", h2d_end, d2h_begin, d2h_end);
+                sparse ? (reuse ? " (sparse D2H, reused buffers)" : " (sparse D2H)") : "", h2d_end, d2h_begin, d2h_end);
+        fprintf(stderr, "[b2r]   host wall: everything enqueued %.2f ms, payload copies issued %.2f, host zeroing done %.2f, scatter done %.2f, call done %.2f\n", w_enq, w_pay,
+                w_zero, w_scat, wall_ms());
         for (auto& e : tev) cudaEventDestroy(e);
     }
     c->last_h2d_bytes = h2d; c->last_d2h_bytes = d2h + (uint64_t)n_slices * sizeof(BatchCounters);
@@ -606,7 +661,7 @@ int b2r_config_new_multi(const b2r_allstr* const* allstr, const b2r_substr* cons
         rc = b2r_config_new(allstr, substrs, n_substrs, n_defs, max_chars_size, device_ids[i], &kid);
         if (rc) { b2r_config_free(parent); return rc; }
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        if (!kid->opt.host_threads) kid->opt.host_threads = (int)std::max(2u, std::min(16u, hw / n_devices));
+        if (!kid->opt.host_threads) kid->opt.host_threads = (int)std::max(2u, std::min(8u, hw / 2 / n_devices));
         m->kids.push_back(kid);
         m->devices.push_back(device_ids[i]);
     }

@@ -228,11 +228,14 @@ class RegexVerifyConfig:
     def new_host_outputs(self, n, **kw):
         return HostOutputs(n, self.max_chars_size, self.state_widths, self.table_num_rows, self.endpoint_num_rows, **kw)
 
-    def match_batch_host(self, data, offsets, out=None, flags=0, check=True, sparse=False, **kw):
+    def match_batch_host(self, data, offsets, out=None, flags=0, check=True, sparse=False, reuse=False, **kw):
         """Host buffers in, host buffers out (H2D, kernels, D2H inside): the call a drop-in shim makes.
-        sparse=True: B2R_OUT_SPARSE_D2H — the zero-dominated columns cross PCIe compacted and are expanded by host threads."""
+        sparse=True: B2R_OUT_SPARSE_D2H — the zero-dominated columns cross PCIe compacted and are expanded by host threads.
+        reuse=True: B2R_OUT_SPARSE_REUSE — `out` is what the previous call on this handle filled: only its sectors are cleared."""
         if sparse:
             flags |= _abi.B2R_OUT_SPARSE_D2H
+        if reuse:
+            flags |= _abi.B2R_OUT_SPARSE_REUSE
         data = np.ascontiguousarray(data, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1

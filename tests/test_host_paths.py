@@ -46,6 +46,32 @@ def test_sparse_d2h_equals_dense_equals_oracle(set_name):
         alloc.free()
 
 
+@pytest.mark.parametrize("set_name", ["regex1", "three"])
+def test_sparse_reuse_clears_only_what_the_last_call_wrote(set_name):
+    """B2R_OUT_SPARSE_REUSE: the same host buffers batch after batch — the library clears the sectors of the previous batch instead
+    of zeroing the columns; different strings every time, a dense-fallback slice in between, a foreign buffer (full zeroing)."""
+    import halo2_regex_b200 as H
+    M = 97
+    rng = random.Random(zlib.crc32(set_name.encode()) + 9)
+    cfg = product_config(set_name, M)
+    kw = dict(max_records=4, compact_pitch=32)
+    n = 18011
+    out = cfg.new_host_outputs(n, fill=0xAB, **kw)
+    other = cfg.new_host_outputs(n, fill=0x77, **kw)
+    for step in range(5):
+        strings = _random_strings(rng, n, M - 1, SNIPPETS)
+        data, offs = _pack(strings, lead=step)
+        o, ores = _oracle(set_name, M, data, offs, **kw)
+        if step == 2:
+            cfg.set_option("sparse_cap", 64)                               # this batch: most column slices cross densely
+        if step == 3:
+            cfg.set_option("sparse_cap", 0)
+        target = other if step == 4 else out                               # step 4: buffers the handle has never seen, still full of 0x77
+        g, gres = cfg.match_batch_host(data, offs, out=target, check=False, sparse=True, reuse=step > 0)
+        assert gres.code == ores.code
+        assert H.compare_outputs(g, o) == [], step
+
+
 def test_sparse_d2h_dense_fallback_and_threads():
     """A column slice with more non-zero sectors than the compaction arena holds crosses densely; any thread count works."""
     import halo2_regex_b200 as H
