@@ -23,6 +23,8 @@ B2R_OUT_ACCUMULATE_MULT = 1
 B2R_OUT_SPARSE_D2H = 2
 B2R_OUT_SPARSE_REUSE = 4
 
+B2R_COL_U8, B2R_COL_U16, B2R_COL_U64, B2R_COL_BITMAP, B2R_COL_CHARS, B2R_COL_ENABLE = 1, 2, 3, 4, 5, 6
+
 
 def B2R_ST_ACCEPTED(d):
     return 1 << d

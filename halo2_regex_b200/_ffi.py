@@ -25,7 +25,7 @@ b2r_config_recommended_bitmap_pitch b2r_table_num_rows b2r_table_rows b2r_endpoi
 b2r_match_batch b2r_batch_result b2r_match_batch_host b2r_match_substrs b2r_match_long b2r_match_long_host b2r_last_launch_count
 b2r_config_set_timing b2r_last_kernel_ms b2r_last_stage_ms b2r_last_plan
 b2r_config_new_multi b2r_config_num_devices b2r_config_set_option b2r_host_alloc b2r_host_free b2r_host_register b2r_host_unregister
-b2r_last_host_bytes
+b2r_last_host_bytes b2r_column_to_fr
 """.split()
 
 
@@ -94,6 +94,7 @@ def _load():
     sig("b2r_host_register", i32, vp, sz)
     sig("b2r_host_unregister", i32, vp)
     sig("b2r_last_host_bytes", i32, vp, pu64, pu64)
+    sig("b2r_column_to_fr", i32, vp, vp, u32, vp, u64, u64, u64, vp, vp)
     return L
 
 

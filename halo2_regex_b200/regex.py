@@ -289,6 +289,29 @@ class RegexVerifyConfig:
             _raise(rc, res)
         return out, res
 
+    # ---- the step after the path: columns as BN254 Fr cells (src/lib.rs:342-347, 388-418: Value::known(F::from(x))) -----------
+    def column_to_fr(self, col, kind=None, rows=None, offsets=None, stream=None):
+        """b2r_column_to_fr: a device column (torch tensor (n, pitch): uint8 -> B2R_COL_U8, int16 -> _U16, int64 -> _U64;
+        kind="bitmap": an LSB-first bitmap column; kind="chars" / "enable": `col` = the input bytes, `offsets` the N+1 offsets) ->
+        int64 tensor (n, rows, 4): little-endian Montgomery limbs of halo2curves::bn256::Fr::from(value)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(col.device)
+        rows = int(rows) if rows else self.max_chars_size
+        kinds = {"u8": _abi.B2R_COL_U8, "u16": _abi.B2R_COL_U16, "u64": _abi.B2R_COL_U64, "bitmap": _abi.B2R_COL_BITMAP,
+                 "chars": _abi.B2R_COL_CHARS, "enable": _abi.B2R_COL_ENABLE}
+        if kind is None:
+            kind = {torch.uint8: "u8", torch.int16: "u16", torch.int64: "u64"}[col.dtype]
+        if kind in ("chars", "enable"):
+            n, pitch = offsets.numel() - 1, 0
+        else:
+            n, pitch = col.shape[0], col.shape[1]
+        out = torch.empty((n, rows, 4), dtype=torch.int64, device=col.device)
+        rc = lib.b2r_column_to_fr(self._h, col.data_ptr(), kinds[kind], offsets.data_ptr() if offsets is not None else None, n, rows, pitch,
+                                  out.data_ptr(), stream.cuda_stream)
+        _raise(rc)
+        return out
+
     def batch_result(self, stream=None, check=True):
         import torch
         if stream is None:

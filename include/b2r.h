@@ -266,6 +266,25 @@ int b2r_match_long(b2r_config* cfg, const uint8_t* d_bytes, uint64_t len, const 
 int b2r_match_long_host(b2r_config* cfg, const uint8_t* h_bytes, uint64_t len, const b2r_outputs* h_out,
                         b2r_batch_status* result);
 
+/* ---- the step after the path: witness columns as field elements ------------------------------------------
+ * The reference places every value of the path in a cell as Value::known(F::from(x as u64)) (src/lib.rs:342-347, 388-418), with
+ * F = halo2curves::bn256::Fr in its own circuits (src/lib.rs:896).  b2r_column_to_fr converts a whole DEVICE column into an array
+ * of Fr in that type's in-memory layout: per cell four little-endian u64 limbs in Montgomery form (x * 2^256 mod r, what
+ * `Fr::from(u64)` = `Fr([x,0,0,0]) * R2` yields), cell (j, i) at d_fr[(j * rows + i) * 4], i < rows, so that a shim can hand
+ * `assign_advice` ready-made field elements (a &[Fr] view of the buffer) instead of converting cell by cell.
+ *   kind B2R_COL_U8 / _U16 / _U64: d_col[j * pitch + i] (pitch in elements); B2R_COL_BITMAP: bit i (LSB first) of row j of a bitmap
+ *   column (pitch in bytes) -> 0 / 1; B2R_COL_CHARS / B2R_COL_ENABLE: d_col = the batch's input bytes, d_offsets its N+1 offsets:
+ *   character_values / enable_values of src/lib.rs:339-348 (the byte, resp. 1, for i < len; 0 after).  d_offsets is ignored otherwise.
+ * Asynchronous on cuda_stream. */
+#define B2R_COL_U8 1u
+#define B2R_COL_U16 2u
+#define B2R_COL_U64 3u
+#define B2R_COL_BITMAP 4u
+#define B2R_COL_CHARS 5u
+#define B2R_COL_ENABLE 6u
+int b2r_column_to_fr(b2r_config* cfg, const void* d_col, uint32_t kind, const uint64_t* d_offsets, uint64_t n_strings, uint64_t rows,
+                     uint64_t pitch, uint64_t* d_fr, void* cuda_stream);
+
 /* kernel launches enqueued by the last b2r_match_* call on this handle (for benchmark accounting) */
 uint32_t b2r_last_launch_count(const b2r_config*);
 /* bytes the last host-pointer call moved over PCIe in each direction */
