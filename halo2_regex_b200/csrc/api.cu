@@ -85,6 +85,7 @@ void read_env_options(b2r_config* c) {
     if (const char* e = getenv("B2R_HIST_CACHE_LOG2")) o.hist_cache_log2 = atoi(e);
     if (const char* e = getenv("B2R_HOST_THREADS")) o.host_threads = atoi(e);
     if (const char* e = getenv("B2R_SMALL_PATH")) o.small_path = atoi(e);
+    if (const char* e = getenv("B2R_LONG_FUSED")) o.long_fused = atoi(e);
 }
 
 }  // namespace
@@ -465,6 +466,9 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     uint32_t max_s1 = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) max_s1 = std::max(max_s1, c->packed[d].num_states + 1);
     const size_t off_uniq = slot((size_t)n_chunks * 4 * 2), off_nuniq = slot(n_chunks), off_which = slot((size_t)n_chunks * max_s1);
+    const uint32_t n_groups = (n_chunks + LONG_GROUP - 1) / LONG_GROUP, n_supers = (n_groups + LONG_SUPER - 1) / LONG_SUPER;
+    const size_t off_summary2 = slot((size_t)((n_chunks + 1023) / 1024) * 4);
+    const size_t off_excl = slot((size_t)n_groups * LONG_FUSED_THREADS * 32), off_agg = slot((size_t)n_groups * 32), off_super = slot((size_t)n_supers * 32), off_scnt = slot((size_t)n_supers * 4);
     if ((rc = c->ws_long.reserve(need))) return rc;
     unsigned char* ws = (unsigned char*)c->ws_long.p;
     uint64_t* d_offsets = (uint64_t*)(ws + off_offsets);
@@ -476,6 +480,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     memset(&lp, 0, sizeof lp);
     lp.bytes = d_bytes; lp.len = len; lp.n_chunks = n_chunks; lp.n_defs = c->n_defs; lp.offsets = d_offsets;
     lp.uniq = (uint16_t*)(ws + off_uniq); lp.n_uniq = ws + off_nuniq; lp.which = ws + off_which;
+    lp.excl = ws + off_excl; lp.agg = ws + off_agg; lp.super = ws + off_super; lp.super_cnt = (uint32_t*)(ws + off_scnt);
     for (uint32_t d = 0; d < c->n_defs; d++) {
         lp.def[d].byte_class = c->dev[d].byte_class; lp.def[d].trans = c->dev[d].trans;
         lp.def[d].num_states = c->packed[d].num_states; lp.def[d].first_state = c->packed[d].first_state;
@@ -499,6 +504,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
         CUDA_TRY(zero(o->masked_substr_ids, col_bytes));
         CUDA_TRY(cudaEventRecord(c->ev_done[0], zs));
     }
+    lp.fused = (c->opt.long_fused && long_fused_ok(lp)) ? 1u : 0u;
     if ((rc = launch_long_prepare(lp, st, &c->last_launches))) return rc;
 
     // ---- 3: the walk, chunk = string, one contiguous state row ------------------------------------------------------------
@@ -526,7 +532,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     pe.fmask = pw.fmask;
     for (uint32_t d = 0; d < c->n_defs; d++) pe.def[d].states = pw.def[d].states;
     c->have_last = true;
-    if ((rc = launch_long_emit(pe, wide, pw.fmask, (uint32_t*)(ws + off_summary), n_chunks, chunk_fm_words, st, &c->last_launches))) return rc;
+    if ((rc = launch_long_emit(pe, wide, pw.fmask, (uint32_t*)(ws + off_summary), (uint32_t*)(ws + off_summary2), n_chunks, chunk_fm_words, st, &c->last_launches))) return rc;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
     rc = enqueue_finalize(c, o, 1, M, st);
     if (rc) return rc;
@@ -552,6 +558,7 @@ int b2r_config_set_option(b2r_config* c, const char* name, const char* value) {
     else if (!strcmp(name, "host_threads")) { o.host_threads = v; c->pool.reset(); }
     else if (!strcmp(name, "small_path")) o.small_path = v;
     else if (!strcmp(name, "sparse_cap")) o.sparse_cap = v;
+    else if (!strcmp(name, "long_fused")) o.long_fused = v;
     else { set_error("unknown option '%s'", name); return B2R_ERR_INVALID_ARG; }
     if (c->multi) return multi_set_option(c->multi, name, value);
     return B2R_OK;

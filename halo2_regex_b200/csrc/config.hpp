@@ -136,6 +136,7 @@ struct b2r_config {
         int hist_cache_log2 = 0;      // 0 = default
         int host_threads = 0;         // sparse D2H mode: host worker threads (0 = default)
         int small_path = 1;           // 0: small batches take the sliced pipeline too (testing hook)
+        int long_fused = 1;           // 0: the long-string path computes the chunk maps with the general multi-kernel pass (testing hook)
         int sparse_cap = 0;           // sparse D2H mode: sectors per column slice before the dense fallback (0 = default; testing hook)
     } opt;
     b2r::DevBuf ws_fmask;                  // granule flags (walk -> emit)

@@ -130,9 +130,15 @@ int launch_walk(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen
     const uint32_t sb = wide ? 2 : 1;
     int warps = WALK_MAX_THREADS / 32;
     while (warps > 1 && walk_smem_bytes(p, sb, warps) > (size_t)max_smem) warps--;
-    const size_t smem = walk_smem_bytes(p, sb, warps);
+    size_t smem = walk_smem_bytes(p, sb, warps);
     if (smem > (size_t)max_smem) { set_error("walk_kernel: %zu bytes of shared memory needed, %d available", smem, max_smem); return B2R_ERR_UNSUPPORTED; }
-    // persistent: one CTA per SM; small batches use fewer CTAs
+    // persistent: one CTA per SM.  A batch of fewer tiles than the SMs have warps is spread over ALL SMs with fewer warps per
+    // CTA (the long-string path: 2048 tiles -> 147 CTAs of 14 warps instead of 128 of 16; every warp still walks one tile)
+    if ((long long)p.n_tiles < (long long)n_sm * warps) {
+        const int per = (int)((p.n_tiles + n_sm - 1) / n_sm);
+        warps = per < 4 ? (warps < 4 ? warps : 4) : per;                   // at least four warps: they also stage the tables
+        smem = walk_smem_bytes(p, sb, warps);
+    }
     const long long ctas = ((long long)p.n_tiles + warps - 1) / warps;
     const int grid = (int)(ctas < n_sm ? (ctas > 0 ? ctas : 1) : n_sm);
     if (chosen) { chosen->grid = grid; chosen->block = warps * 32; chosen->smem_bytes = smem; }

@@ -250,25 +250,295 @@ __global__ void __launch_bounds__(256) long_resolve_kernel(const uint16_t* maps,
     entry0[c] = (uint16_t)s;
 }
 
+// ---- fused prefix pass (small DFAs) ------------------------------------------------------------------------------------------
+// ONE kernel computes every chunk's transition vector and the exclusive prefixes inside groups of LONG_GROUP chunks, a second
+// (tiny) one pushes first_state through the group aggregates: 2 launches instead of 9.
+//   thread = half a chunk.  All S states walk rounds of 32 bytes until at most 4 distinct images are left (the shipped DFAs collapse
+//   in the first round), which then walk the rest of the chunk together; every lookup goes to BANK-REPLICATED tables (entry of
+//   lane l in bank l, as in walk.cuh): 32 chunks with arbitrary bytes and states, one wavefront per lookup.
+//   cls_r[byte][lane] = absolute shared address of (class row, state 0, this lane); tr_r[(class * P + state)][lane] = next state * 128.
+template <int SP>
+__global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 4 : 3) long_maps_fused_kernel(const __grid_constant__ LongParams p, uint32_t d, uint32_t P, uint32_t n_groups) {
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    __shared__ uint32_t is_last, absorbing_s;
+    __shared__ uint8_t wagg[(LONG_FUSED_THREADS / 32) * 32];              // aggregate of every warp's 32 maps
+    const uint32_t S = p.def[d].num_states, C = p.def[d].num_classes;
+    uint32_t* tr_r = reinterpret_cast<uint32_t*>(long_smem);
+    uint16_t* cls_r = reinterpret_cast<uint16_t*>(tr_r + (size_t)C * P * 32);  // [256][32] class of the byte, one copy per lane (16 KB)
+    uint8_t* maps = reinterpret_cast<uint8_t*>(cls_r + 256 * 32);            // [LONG_FUSED_THREADS][SP]
+    const uint32_t lane = threadIdx.x & 31;
+    {
+        // the compact tables first (coalesced), then their per-lane copies out of shared memory
+        const bool staged = (size_t)C * S * 4 + 256 <= (size_t)LONG_FUSED_THREADS * SP;
+        uint32_t* tmp_tr = reinterpret_cast<uint32_t*>(maps + 256);
+        if (threadIdx.x == 0) absorbing_s = 0;
+        if (staged) {
+            for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) maps[i] = p.def[d].byte_class[i];
+            for (uint32_t i = threadIdx.x; i < C * S; i += blockDim.x) tmp_tr[i] = p.def[d].trans[i];
+        }
+        __syncthreads();
+        // absorbing states (every class leads back to the state itself, e.g. an accepting sink): their image never has to be walked
+        if (threadIdx.x < S) {
+            bool fixed = true;
+            for (uint32_t c = 0; c < C; c++) {
+                const uint32_t t = staged ? tmp_tr[c * S + threadIdx.x] : p.def[d].trans[c * S + threadIdx.x];
+                fixed = fixed && !(t & ENT_INVALID) && (t & ENT_NEXT_MASK) == threadIdx.x;
+            }
+            if (fixed) atomicOr(&absorbing_s, 1u << threadIdx.x);
+        }
+        for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) cls_r[i] = staged ? maps[i >> 5] : p.def[d].byte_class[i >> 5];
+        for (uint32_t i = threadIdx.x; i < C * P * 32; i += blockDim.x) {
+            const uint32_t e = i >> 5, c = e / P, st = e % P;
+            uint32_t nx = S;                                              // trap state: sticky, also the image of every invalid transition
+            if (st < S) { const uint32_t t = staged ? tmp_tr[c * S + st] : p.def[d].trans[c * S + st]; nx = (t & ENT_INVALID) ? S : (t & ENT_NEXT_MASK); }
+            tr_r[i] = nx * 128u;
+        }
+        __syncthreads();
+    }
+    const uint32_t absorbing = absorbing_s | (1u << S);                   // the trap state is sticky too
+    const uint32_t tr_lane = (uint32_t)__cvta_generic_to_shared(tr_r) + lane * 4;
+    const uint32_t cls_lane = (uint32_t)__cvta_generic_to_shared(cls_r) + lane * 2;
+    const uint32_t rowb = P * 128u;
+    // the tables are read-only from here on: plain (movable) loads, so that the class rows of a whole vector of bytes are
+    // looked up ahead of the dependent chain of state lookups (issue is in order: a class lookup inside the chain would stall it)
+    auto lds = [](uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+    // absolute shared address of (class row of `byte`, state 0, this lane)
+    auto row_of = [&](uint32_t byte) { uint32_t k; asm("ld.shared.u16 %0, [%1];" : "=r"(k) : "r"(cls_lane + byte * 64u)); return tr_lane + k * rowb; };
+    // every thread streams through its own half chunk 16 bytes at a time: the loads ask L2 for the whole 128-byte line
+    auto ldv = [](const uint8_t* q) { uint4 v; asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q)); return v; };
+
+    for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        // thread = sub-chunk of LONG_SUB bytes (half a chunk: twice the warps for the same chains)
+        const uint32_t k = grp * LONG_FUSED_THREADS + threadIdx.x;
+        if ((k & 1u) == 0 && (k >> 1) < p.n_chunks) p.offsets[k >> 1] = (uint64_t)(k >> 1) * LONG_CHUNK;   // chunk offsets for the walk kernel
+        if (k == 0) p.offsets[p.n_chunks] = p.len;
+        uint32_t st[SP];
+#pragma unroll
+        for (int s = 0; s < SP; s++) st[s] = ((uint32_t)s < S ? (uint32_t)s : S) * 128u;
+        uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0, n = SP + 1;
+        uint64_t which = 0;
+        if ((uint64_t)k * LONG_SUB < p.len) {
+            const uint64_t a = (uint64_t)k * LONG_SUB;
+            const uint64_t b = a + LONG_SUB < p.len ? a + LONG_SUB : p.len;
+            uint64_t i = a;
+            // ---- all states, 16 bytes per round, until at most 4 distinct images are left --------------------------------------
+            while (i < b) {
+                const uint64_t e = i + 16 < b ? i + 16 : b;
+                if (e - i == 16) {
+                    const uint4 v0 = ldv(p.bytes + i);
+                    const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t rows[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) rows[j] = row_of((w[q] >> (8 * j)) & 255u);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+#pragma unroll
+                            for (int s = 0; s < SP; s++) st[s] = lds(rows[j] + st[s]);
+                        }
+                    }
+                } else {
+                    for (uint64_t t = i; t < e; t++) {
+                        const uint32_t cabs = row_of((uint32_t)__ldg(p.bytes + t));
+#pragma unroll
+                        for (int s = 0; s < SP; s++) st[s] = lds(cabs + st[s]);
+                    }
+                }
+                i = e;
+                n = 0; which = 0;
+#pragma unroll
+                for (int s = 0; s < SP; s++) {
+                    if ((uint32_t)s >= S) continue;                     // real states only: the trap state maps to itself
+                    const uint32_t v = st[s];
+                    uint32_t j = (n > 0 && v == u0) ? 0u : (n > 1 && v == u1) ? 1u : (n > 2 && v == u2) ? 2u : (n > 3 && v == u3) ? 3u : 4u;
+                    if (j == 4u) {
+                        if (n == 0) u0 = v; else if (n == 1) u1 = v; else if (n == 2) u2 = v; else if (n == 3) u3 = v;
+                        j = n; n++;
+                    }
+                    which |= (uint64_t)(j & 3u) << (2 * s);
+                }
+                if (n <= 4) break;
+            }
+            // ---- the distinct images walk the rest together; an image that is an absorbing state stays where it is ---------------------
+            if (n <= 4 && i < b) {
+                if (n < 4) u3 = S * 128u;
+                if (n < 3) u2 = S * 128u;
+                if (n < 2) u1 = S * 128u;
+                const bool f0 = (absorbing >> (u0 >> 7)) & 1u, f1 = (absorbing >> (u1 >> 7)) & 1u, f2 = (absorbing >> (u2 >> 7)) & 1u, f3 = (absorbing >> (u3 >> 7)) & 1u;
+                const uint32_t moving = (f0 ? 0u : 1u) + (f1 ? 0u : 1u) + (f2 ? 0u : 1u) + (f3 ? 0u : 1u);
+                // the moving images first (a, b; all four when more than two move)
+                uint32_t wa = u0, wb = u1;
+                int ia = 0, ib = 1;
+                if (moving <= 2) {
+                    ia = !f0 ? 0 : !f1 ? 1 : !f2 ? 2 : 3;                  // first moving image (any when none moves)
+                    ib = ia;
+                    if (moving == 2) ib = (!f1 && ia < 1) ? 1 : (!f2 && ia < 2) ? 2 : 3;
+                    wa = ia == 0 ? u0 : ia == 1 ? u1 : ia == 2 ? u2 : u3;
+                    wb = ib == 0 ? u0 : ib == 1 ? u1 : ib == 2 ? u2 : u3;
+                }
+                auto walk_rest = [&](auto width_tag) {
+                    constexpr int W = decltype(width_tag)::value;         // 1, 2: wa (, wb); 4: u0..u3
+                    auto step_row = [&](uint32_t cabs) {
+                        if (W == 4) { u0 = lds(cabs + u0); u1 = lds(cabs + u1); u2 = lds(cabs + u2); u3 = lds(cabs + u3); }
+                        else { wa = lds(cabs + wa); if (W == 2) wb = lds(cabs + wb); }
+                    };
+                    auto step = [&](uint32_t byte) { step_row(row_of(byte)); };
+                    auto step16 = [&](const uint4& v) {
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t rows[16];
+#pragma unroll
+                        for (int q = 0; q < 16; q++) rows[q] = row_of((w[q >> 2] >> (8 * (q & 3))) & 255u);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) step_row(rows[q]);
+                    };
+                    if (i + 64 <= b) {                                    // 64 bytes per round, the next round's vectors in flight
+                        const uint8_t* q = p.bytes + i;
+                        uint4 n0 = ldv(q), n1 = ldv(q + 16), n2 = ldv(q + 32), n3 = ldv(q + 48);
+                        for (; i + 64 <= b; i += 64) {
+                            const uint4 v0 = n0, v1 = n1, v2 = n2, v3 = n3;
+                            if (i + 128 <= b) { q = p.bytes + i + 64; n0 = ldv(q); n1 = ldv(q + 16); n2 = ldv(q + 32); n3 = ldv(q + 48); }
+                            step16(v0); step16(v1); step16(v2); step16(v3);
+                        }
+                    }
+                    for (; i + 16 <= b; i += 16) step16(ldv(p.bytes + i));
+                    for (; i < b; i++) step(__ldg(p.bytes + i));
+                };
+                if (moving > 2) walk_rest(std::integral_constant<int, 4>{});
+                else {
+                    if (moving == 2) walk_rest(std::integral_constant<int, 2>{});
+                    else if (moving == 1) walk_rest(std::integral_constant<int, 1>{});
+                    if (moving >= 1) { if (ia == 0) u0 = wa; else if (ia == 1) u1 = wa; else if (ia == 2) u2 = wa; else u3 = wa; }
+                    if (moving == 2) { if (ib == 1) u1 = wb; else if (ib == 2) u2 = wb; else u3 = wb; }
+                }
+            }
+        }
+        // the chunk's transition vector as state indices (chunks past the end of the string, and an empty string: the identity)
+        uint8_t* mine = maps + threadIdx.x * SP;
+#pragma unroll
+        for (int s = 0; s < SP; s++) {
+            uint32_t v = st[s];
+            if (n <= 4) { const uint32_t j = (uint32_t)(which >> (2 * s)) & 3u; v = j == 0 ? u0 : j == 1 ? u1 : j == 2 ? u2 : u3; }
+            if ((uint32_t)s >= S) v = S * 128u;
+            mine[s] = (uint8_t)(v >> 7);
+        }
+        __syncthreads();
+        // ---- exclusive prefixes inside the group, in place, and the group aggregate: every warp scans its own 32 maps (lane =
+        //      state), the warp aggregates are combined, and every warp applies the prefix of the warps before it ------------------
+        {
+            const uint32_t warp = threadIdx.x >> 5, c0 = warp * 32;
+            uint32_t cur = lane < SP ? lane : 0u;
+            for (uint32_t c = c0; c < c0 + 32; c++) {
+                const uint32_t nxt = lane < SP ? maps[c * SP + cur] : 0u;
+                __syncwarp();
+                if (lane < SP) maps[c * SP + lane] = (uint8_t)cur;
+                __syncwarp();
+                cur = nxt;
+            }
+            if (lane < SP) wagg[warp * SP + lane] = (uint8_t)cur;
+            __syncthreads();
+            uint32_t pw = lane < SP ? lane : 0u;                           // composition of the warps in front of mine
+            for (uint32_t v = 0; v < warp; v++) pw = wagg[v * SP + pw];
+            if (warp > 0) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t val[16];
+#pragma unroll
+                    for (int c = 0; c < 16; c++) val[c] = lane < SP ? maps[(c0 + 16 * h + c) * SP + pw] : 0u;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 16; c++) if (lane < SP) maps[(c0 + 16 * h + c) * SP + lane] = (uint8_t)val[c];
+                    __syncwarp();
+                }
+            }
+            if (warp == LONG_FUSED_THREADS / 32 - 1 && lane < SP) { p.agg[(size_t)grp * SP + lane] = wagg[warp * SP + pw]; __threadfence(); }
+        }
+        __syncthreads();
+        {
+            uint4* dst = reinterpret_cast<uint4*>(p.excl + (size_t)grp * LONG_FUSED_THREADS * SP);
+            const uint4* src = reinterpret_cast<const uint4*>(maps);
+            for (uint32_t i = threadIdx.x; i < LONG_FUSED_THREADS * SP / 16; i += blockDim.x) dst[i] = src[i];
+        }
+        // ---- the last group of a super group to arrive composes the super group's aggregate --------------------------------------------
+        const uint32_t sg = grp / LONG_SUPER;
+        const uint32_t g0 = sg * LONG_SUPER, g1 = g0 + LONG_SUPER < n_groups ? g0 + LONG_SUPER : n_groups;
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); is_last = atomicAdd(p.super_cnt + sg, 1u) == g1 - g0 - 1u; }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            // the group aggregates in one round trip (the maps buffer is free again), then the chain in shared memory
+            for (uint32_t i = threadIdx.x; i < (g1 - g0) * SP; i += blockDim.x) maps[i] = __ldcg(p.agg + (size_t)g0 * SP + i);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t cur = lane < SP ? lane : 0u;
+                for (uint32_t g = 0; g < g1 - g0; g++) cur = maps[g * SP + cur];
+                if (lane < SP) p.super[(size_t)sg * SP + lane] = (uint8_t)cur;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// entry state of every chunk: first_state through the super-group aggregates, then the group aggregates, then the chunk's exclusive
+// prefix inside its group; CTA per group
+__global__ void __launch_bounds__(LONG_GROUP) long_entry_kernel(const __grid_constant__ LongParams p, uint32_t d, uint32_t SP) {
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    __shared__ uint32_t entry_s;
+    const uint32_t b = blockIdx.x, sg = b / LONG_SUPER, g0 = sg * LONG_SUPER;
+    const uint32_t n_stage = (sg + (b - g0)) * SP;                         // supers [0, sg), then groups [g0, b)
+    for (uint32_t i = threadIdx.x; i < n_stage; i += blockDim.x)
+        long_smem[i] = i < sg * SP ? __ldcg(p.super + i) : __ldcg(p.agg + (size_t)g0 * SP + (i - sg * SP));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = p.def[d].first_state;
+        for (uint32_t t = 0; t < sg + (b - g0); t++) s = long_smem[t * SP + s];
+        entry_s = s;
+    }
+    __syncthreads();
+    const uint32_t k = b * LONG_GROUP + threadIdx.x;
+    if (k < p.n_chunks) p.def[d].entry[k] = (uint16_t)__ldcg(p.excl + (size_t)k * (LONG_CHUNK / LONG_SUB) * SP + entry_s);   // the prefix in front of its first sub-chunk
+}
+
+static size_t long_fused_smem(uint32_t C, uint32_t P, uint32_t SP) { return (size_t)256 * 64 + (size_t)C * P * 128 + (size_t)LONG_FUSED_THREADS * SP; }
+static uint32_t long_padded(uint32_t S1) { uint32_t P = 1; while (P < S1) P <<= 1; return P; }
+
+bool long_fused_ok(const LongParams& lp) {
+    int n_sm = 0, max_smem = 0;
+    if (device_limits(&n_sm, &max_smem)) return false;
+    for (uint32_t d = 0; d < lp.n_defs; d++) {
+        const uint32_t S1 = lp.def[d].num_states + 1;
+        if (S1 > 32) return false;
+        if (long_fused_smem(lp.def[d].num_classes, long_padded(S1), S1 <= 16 ? 16 : 32) > (size_t)max_smem) return false;
+        if ((uint64_t)((lp.n_chunks + LONG_GROUP - 1) / LONG_GROUP / LONG_SUPER + LONG_SUPER) * 32 > 160 * 1024) return false;   // staging area of long_entry_kernel
+    }
+    return true;
+}
+
 // bit c of word w: chunk 32w + c has a flagged granule
-__global__ void __launch_bounds__(256) long_summary_kernel(const uint32_t* fmask, uint32_t fm_words, uint32_t n_chunks, uint32_t* summary) {
+// bit w of summary2 word v: summary word 32v + w is non-zero (summary2 is zeroed before the launch)
+__global__ void __launch_bounds__(256) long_summary_kernel(const uint32_t* fmask, uint32_t fm_words, uint32_t n_chunks, uint32_t* summary, uint32_t* summary2) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t any = 0;
     if (c < n_chunks)
         for (uint32_t w = 0; w < fm_words; w++) any |= fmask[(size_t)w * n_chunks + c];
     const uint32_t word = __ballot_sync(0xffffffffu, any != 0);
-    if ((threadIdx.x & 31) == 0 && c < n_chunks) summary[c >> 5] = word;
+    if ((threadIdx.x & 31) == 0 && c < n_chunks) {
+        summary[c >> 5] = word;
+        if (word) atomicOr(summary2 + (c >> 10), 1u << ((c >> 5) & 31u));
+    }
 }
 
 // One warp: the emit stage of the single long string.  `p` describes the string as ONE string (n_strings = 1, offsets = {0, len},
 // max_chars = len + 1); fmask holds the granule flags per chunk: word w of chunk c at fmask[w * n_chunks + c].
 template <int D, typename ST>
-__global__ void __launch_bounds__(32) long_emit_kernel(const __grid_constant__ WalkParams p, const uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words) {
+__global__ void __launch_bounds__(128) long_emit_kernel(const __grid_constant__ WalkParams p, const uint32_t* summary, const uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words) {
     extern __shared__ __align__(16) unsigned char esmem[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     EmitTables<D> tb;
-    emit_tables_init<D>(p, esmem, tb);
+    emit_tables_init<D>(p, esmem, tb);                                  // all four warps stage the tables; warp 0 does the (ordered) work
     __syncthreads();
+    if (threadIdx.x < 32) {
     const uint32_t L = p.max_chars - 1;
     constexpr uint32_t GPC = LONG_CHUNK / 16;                            // granules per chunk
     LaneString<D, ST> ls(p, tb, 0, p.bytes, L);
@@ -278,29 +548,38 @@ __global__ void __launch_bounds__(32) long_emit_kernel(const __grid_constant__ W
         constexpr bool PATCH = decltype(patch_tag)::value;
         ls.scan_begin();
         bool stop = false;                                               // warp-uniform: lane 0 hit an invalid transition
-        const uint32_t n_words = (n_chunks + 31) / 32;
-        for (uint32_t w0 = 0; w0 < n_words && !stop; w0 += 32) {         // 32 summary words at a time, one per lane
-            const uint32_t mine = w0 + lane < n_words ? summary[w0 + lane] : 0u;
-            uint32_t lanes = __ballot_sync(0xffffffffu, mine != 0);
-            while (lanes && !stop) {
-                const int l = __ffs((int)lanes) - 1;
-                lanes &= lanes - 1;
-                uint32_t chunks = __shfl_sync(0xffffffffu, mine, l);
-                while (chunks && !stop) {
-                    const uint32_t c = (w0 + l) * 32 + ((uint32_t)__ffs((int)chunks) - 1u);
-                    chunks &= chunks - 1;
-                    if (lane == 0) {
-                        for (uint32_t w = 0; w < chunk_fm_words && !ls.invalid; w++) {
-                            const uint32_t fw = p.fmask[(size_t)w * n_chunks + c];
-                            uint32_t bits = fw;
-                            while (bits && !ls.invalid) {
-                                const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
-                                bits &= bits - 1;
-                                ls.template scan_granule<PATCH>(c * GPC + w * 32 + g, (fw >> (g ^ 1u)) & 1u);
+        const uint32_t n_words = (n_chunks + 31) / 32, n_words2 = (n_words + 31) / 32;
+        // second level first, 32 words per load: stretches of 1024 chunks without a flagged granule cost nothing
+        for (uint32_t v0 = 0; v0 < n_words2 && !stop; v0 += 32) {
+            const uint32_t mine2 = v0 + lane < n_words2 ? __ldcg(summary2 + v0 + lane) : 0u;
+            uint32_t lanes2 = __ballot_sync(0xffffffffu, mine2 != 0);
+            while (lanes2 && !stop) {
+                const int l2 = __ffs((int)lanes2) - 1;
+                lanes2 &= lanes2 - 1;
+                const uint32_t lvl2 = __shfl_sync(0xffffffffu, mine2, l2);
+                const uint32_t w0 = (v0 + (uint32_t)l2) * 32;                // 32 summary words, one per lane
+                const uint32_t mine = (w0 + lane < n_words && ((lvl2 >> lane) & 1u)) ? __ldcg(summary + w0 + lane) : 0u;
+                uint32_t lanes = __ballot_sync(0xffffffffu, mine != 0);
+                while (lanes && !stop) {
+                    const int l = __ffs((int)lanes) - 1;
+                    lanes &= lanes - 1;
+                    uint32_t chunks = __shfl_sync(0xffffffffu, mine, l);
+                    while (chunks && !stop) {
+                        const uint32_t c = (w0 + l) * 32 + ((uint32_t)__ffs((int)chunks) - 1u);
+                        chunks &= chunks - 1;
+                        if (lane == 0) {
+                            for (uint32_t w = 0; w < chunk_fm_words && !ls.invalid; w++) {
+                                const uint32_t fw = p.fmask[(size_t)w * n_chunks + c];
+                                uint32_t bits = fw;
+                                while (bits && !ls.invalid) {
+                                    const uint32_t g = (uint32_t)__ffs((int)bits) - 1u;
+                                    bits &= bits - 1;
+                                    ls.template scan_granule<PATCH>(c * GPC + w * 32 + g, (fw >> (g ^ 1u)) & 1u);
+                                }
                             }
                         }
+                        stop = __shfl_sync(0xffffffffu, (int)ls.invalid, 0) != 0;
                     }
-                    stop = __shfl_sync(0xffffffffu, (int)ls.invalid, 0) != 0;
                 }
             }
         }
@@ -344,6 +623,7 @@ __global__ void __launch_bounds__(32) long_emit_kernel(const __grid_constant__ W
             if (r_flags & B2R_ST_OVERLAP) atomicAdd(&p.counters->n_overlap, 1ull);
         }
     }
+    }
     EmitTotals none;
     emit_publish<D>(p, tb, none);
 }
@@ -364,11 +644,34 @@ size_t long_level_nodes(uint32_t n_chunks) {
 // chunk offsets, chunk maps, the composition tree and the entry states of every chunk (level 0 of `entry`)
 int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) {
     cudaStream_t st = (cudaStream_t)stream;
-    long_offsets_kernel<<<(lp.n_chunks + 1 + 255) / 256, 256, 0, st>>>(lp.offsets, lp.n_chunks, lp.len);
-    LAUNCH_CHECK("long_offsets_kernel"); (*launches)++;
+    if (!lp.fused) {   // the fused pass writes the chunk offsets itself
+        long_offsets_kernel<<<(lp.n_chunks + 1 + 255) / 256, 256, 0, st>>>(lp.offsets, lp.n_chunks, lp.len);
+        LAUNCH_CHECK("long_offsets_kernel"); (*launches)++;
+    }
     for (uint32_t d = 0; d < lp.n_defs; d++) {
         const uint32_t S1 = lp.def[d].num_states + 1;
         const uint64_t threads = (uint64_t)lp.n_chunks * S1;
+        if (lp.fused) {
+            int n_sm = 0, max_smem = 0;
+            { const int rc = device_limits(&n_sm, &max_smem); if (rc) return rc; }
+            const uint32_t SP = S1 <= 16 ? 16u : 32u, P = long_padded(S1);
+            const uint32_t n_groups = (lp.n_chunks + LONG_GROUP - 1) / LONG_GROUP, n_supers = (n_groups + LONG_SUPER - 1) / LONG_SUPER;
+            const size_t smem = long_fused_smem(lp.def[d].num_classes, P, SP);
+            if (cudaMemsetAsync(lp.super_cnt, 0, (size_t)n_supers * 4, st) != cudaSuccess) { set_error("cudaMemsetAsync(super_cnt)"); return B2R_ERR_CUDA; }
+            auto kern = SP == 16 ? long_maps_fused_kernel<16> : long_maps_fused_kernel<32>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("cudaFuncSetAttribute(long_maps_fused_kernel)"); return B2R_ERR_CUDA; }
+            // resident CTAs only (equal work per group: a static stride balances): the tables are staged once per CTA
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)LONG_FUSED_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            const uint32_t grid = std::min<uint32_t>(n_groups, (uint32_t)(n_sm * per_sm));
+            kern<<<grid, LONG_FUSED_THREADS, smem, st>>>(lp, d, P, n_groups);
+            LAUNCH_CHECK("long_maps_fused_kernel"); (*launches)++;
+            const size_t esmem = (size_t)(n_supers + LONG_SUPER) * SP;
+            if (esmem > 48 * 1024 && cudaFuncSetAttribute(long_entry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem) != cudaSuccess) { set_error("cudaFuncSetAttribute(long_entry_kernel)"); return B2R_ERR_CUDA; }
+            long_entry_kernel<<<n_groups, LONG_GROUP, esmem, st>>>(lp, d, SP);
+            LAUNCH_CHECK("long_entry_kernel"); (*launches)++;
+            continue;
+        }
         // tables in shared memory when they fit (and class * (S+1) fits the u16 of the class table)
         int n_sm = 0, max_smem = 0;
         { const int rc = device_limits(&n_sm, &max_smem); if (rc) return rc; }
@@ -439,24 +742,25 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
 }
 
 template <int D, typename ST>
-static int launch_long_emit_one(const WalkParams& p, const uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, cudaStream_t st) {
+static int launch_long_emit_one(const WalkParams& p, const uint32_t* summary, const uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, cudaStream_t st) {
     const size_t smem = emit_smem_bytes(p);
     auto kern = long_emit_kernel<D, ST>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(long_emit_kernel): %s", cudaGetErrorString(e)); return B2R_ERR_CUDA; }
     }
-    kern<<<1, 32, smem, st>>>(p, summary, n_chunks, chunk_fm_words);
+    kern<<<1, 128, smem, st>>>(p, summary, summary2, n_chunks, chunk_fm_words);
     LAUNCH_CHECK("long_emit_kernel");
     return B2R_OK;
 }
 
-int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches) {
+int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches) {
     cudaStream_t st = (cudaStream_t)stream;
-    long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary);
+    if (cudaMemsetAsync(summary2, 0, (size_t)((n_chunks + 1023) / 1024) * 4, st) != cudaSuccess) { set_error("cudaMemsetAsync(summary2)"); return B2R_ERR_CUDA; }
+    long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary, summary2);
     LAUNCH_CHECK("long_summary_kernel"); (*launches)++;
     (*launches)++;
-#define GO(D_) return wide ? launch_long_emit_one<D_, uint16_t>(p, summary, n_chunks, chunk_fm_words, st) : launch_long_emit_one<D_, uint8_t>(p, summary, n_chunks, chunk_fm_words, st)
+#define GO(D_) return wide ? launch_long_emit_one<D_, uint16_t>(p, summary, summary2, n_chunks, chunk_fm_words, st) : launch_long_emit_one<D_, uint8_t>(p, summary, summary2, n_chunks, chunk_fm_words, st)
     switch (p.n_defs) {
         case 1: GO(1);
         case 2: GO(2);

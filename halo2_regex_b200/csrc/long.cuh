@@ -40,11 +40,28 @@ struct LongParams {
     uint16_t* uniq;                      // [n_chunks][4]
     uint8_t* n_uniq;                     // [n_chunks]
     uint8_t* which;                      // [n_chunks][max S + 1]
+    // fused prefix pass (small DFAs, long_fused_ok): per group of LONG_GROUP chunks the exclusive prefixes of the chunk maps
+    // [n_chunks][SP] (SP = 16 or 32 bytes per map), the group aggregates [n_groups][SP], the aggregates of LONG_SUPER groups
+    // [n_supers][SP], and one arrival counter per super group (zeroed before the pass)
+    uint8_t* excl;
+    uint8_t* agg;
+    uint8_t* super;
+    uint32_t* super_cnt;
+    uint32_t fused;                      // 1: the fused pass is used (decided by long_plan)
 };
+
+constexpr uint32_t LONG_GROUP = 128;       // chunks per CTA of the fused prefix pass
+constexpr uint32_t LONG_SUB = 512;         // bytes per thread of the fused prefix pass (a sub-chunk)
+constexpr uint32_t LONG_FUSED_THREADS = LONG_GROUP * (LONG_CHUNK / LONG_SUB);
+constexpr uint32_t LONG_SUPER = 32;        // groups per super group
+
+// fused prefix pass: usable when every def has at most 31 states and its bank-replicated tables fit next to four CTAs' maps
+bool long_fused_ok(const LongParams& lp);
 
 // host-callable (long.cu)
 int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches);
-int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches);
+// summary: one bit per chunk ("has a flagged granule"), followed by summary2: one bit per summary word (zeroed by the caller)
+int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches);
 size_t long_level_nodes(uint32_t n_chunks);   // total nodes over all tree levels
 
 }  // namespace b2r

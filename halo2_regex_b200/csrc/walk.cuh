@@ -67,7 +67,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory"); }
 // 16-byte async copy global -> shared; copies src_bytes (0..16) and zero-fills the rest
 __device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -401,11 +401,18 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         uint32_t before[D][4];                          // the entry that led to the state of row 4q + j
+                        // the class lookups of the word first: they do not depend on the state, and issue is in order — inside the
+                        // chain each of them would add its latency to the dependent state lookup behind it
+                        uint32_t cw[4], centw[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const uint32_t c = prmt(w[q], 0u, 0x4440u + j);
-                            uint32_t cent = 0;
-                            if (SMEM_TAB) cent = lds32(cls_lane_s + c * cstride);
+                            cw[j] = prmt(w[q], 0u, 0x4440u + j);
+                            centw[j] = 0;
+                            if (SMEM_TAB) centw[j] = lds32(cls_lane_s + cw[j] * cstride);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t c = cw[j], cent = centw[j];
 #pragma unroll
                             for (int d = 0; d < D; d++) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);

@@ -409,6 +409,44 @@ def test_long_string_16_mib_bit_exact():
     assert int(g.mult[0].sum()) == M
 
 
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("length", [1, 4097, 300000])
+def test_long_string_counter_dfa_never_collapses(length, fused):
+    """A DFA whose states never merge (x: s -> s+1 mod 7, y: s -> s): every chunk keeps 7 distinct images, so the fused prefix pass
+    stays on its all-states rounds and the general pass on its wide-chunk path; both against the oracle.  Also the shipped DFAs
+    through the general (multi-kernel) pass, which the fused one replaces by default."""
+    import torch
+    import halo2_regex_b200 as H
+    from oracle import oracle as O
+    S = 7
+    allstr = f"0\n3\n{S - 1}\n" + "".join(f"{s} {(s + 1) % S} {ord('x')}\n{s} {s} {ord('y')}\n" for s in range(S))
+    substr = "64\n0\n64\n2\n5\n2 3\n3 4\n4 5\n3 3\n4 4\n"
+    rng = random.Random(length)
+    s = bytes(rng.choice(b"xyyy") for _ in range(length))
+    M = length + 1
+    cfg = H.RegexVerifyConfig.configure(64, [H.RegexDefs(H.AllstrRegexDef.read_from_reader(allstr.encode()), [H.SubstrRegexDef.read_from_reader(substr.encode())])])
+    cfg.set_option("long_fused", fused)
+    ocfg = O.OracleConfig([(O.OracleAllstr(allstr), [O.OracleSubstr(substr)])], M)
+    g, gres = cfg.match_long_host(s, check=False, max_records=16, compact_pitch=128)
+    data, offs = _pack([s])
+    o, ores = ocfg.match_batch(data, offs, max_records=16, compact_pitch=128)
+    assert gres.code == ores.code == 0
+    assert H.compare_outputs(g, o) == []
+    # the shipped DFAs through the other pass
+    for set_name in ("regex2", "test1"):
+        body = bytearray(rng.choice(b"abc xyz.@\r\n") for _ in range(length))
+        for snip in SNIPPETS[:6]:
+            if length > 200:
+                at = rng.randrange(0, length - len(snip))
+                body[at:at + len(snip)] = snip
+        c2 = product_config(set_name, 64)
+        c2.set_option("long_fused", fused)
+        g2, r2 = c2.match_long_host(bytes(body), check=False, max_records=16, compact_pitch=128)
+        d2, f2 = _pack([bytes(body)])
+        o2, or2 = oracle_config(set_name, M).match_batch(d2, f2, max_records=16, compact_pitch=128)
+        assert r2.code == or2.code and H.compare_outputs(g2, o2) == []
+
+
 def test_long_string_invalid_transition():
     import torch
     import halo2_regex_b200 as H
