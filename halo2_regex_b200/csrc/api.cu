@@ -467,8 +467,10 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     for (uint32_t d = 0; d < c->n_defs; d++) max_s1 = std::max(max_s1, c->packed[d].num_states + 1);
     const size_t off_uniq = slot((size_t)n_chunks * 4 * 2), off_nuniq = slot(n_chunks), off_which = slot((size_t)n_chunks * max_s1);
     const uint32_t n_groups = (n_chunks + LONG_GROUP - 1) / LONG_GROUP, n_supers = (n_groups + LONG_SUPER - 1) / LONG_SUPER;
-    const size_t off_summary2 = slot((size_t)((n_chunks + 1023) / 1024) * 4);
-    const size_t off_excl = slot((size_t)n_groups * LONG_FUSED_THREADS * 32), off_agg = slot((size_t)n_groups * 32), off_super = slot((size_t)n_supers * 32), off_scnt = slot((size_t)n_supers * 4);
+    // one zeroed block: the arrival counters of the super groups (per def) and the second level of the flag summary
+    const size_t n_words2 = (n_chunks + 1023) / 1024;
+    const size_t off_scnt = slot(((size_t)n_supers * B2R_MAX_DEFS + n_words2) * 4), off_summary2 = off_scnt + (size_t)n_supers * B2R_MAX_DEFS * 4;
+    const size_t off_excl = slot((size_t)n_groups * LONG_FUSED_THREADS * 32), off_agg = slot((size_t)n_groups * 32), off_super = slot((size_t)n_supers * 32);
     if ((rc = c->ws_long.reserve(need))) return rc;
     unsigned char* ws = (unsigned char*)c->ws_long.p;
     uint64_t* d_offsets = (uint64_t*)(ws + off_offsets);
@@ -505,6 +507,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
         CUDA_TRY(cudaEventRecord(c->ev_done[0], zs));
     }
     lp.fused = (c->opt.long_fused && long_fused_ok(lp)) ? 1u : 0u;
+    CUDA_TRY(cudaMemsetAsync(ws + off_scnt, 0, ((size_t)n_supers * B2R_MAX_DEFS + n_words2) * 4, st));
     if ((rc = launch_long_prepare(lp, st, &c->last_launches))) return rc;
 
     // ---- 3: the walk, chunk = string, one contiguous state row ------------------------------------------------------------

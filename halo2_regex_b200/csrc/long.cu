@@ -258,14 +258,14 @@ __global__ void __launch_bounds__(256) long_resolve_kernel(const uint16_t* maps,
 //   lane l in bank l, as in walk.cuh): 32 chunks with arbitrary bytes and states, one wavefront per lookup.
 //   cls_r[byte][lane] = absolute shared address of (class row, state 0, this lane); tr_r[(class * P + state)][lane] = next state * 128.
 template <int SP>
-__global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 4 : 3) long_maps_fused_kernel(const __grid_constant__ LongParams p, uint32_t d, uint32_t P, uint32_t n_groups) {
+__global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 2 : 1) long_maps_fused_kernel(const __grid_constant__ LongParams p, uint32_t d, uint32_t P, uint32_t n_groups) {
     extern __shared__ __align__(16) unsigned char long_smem[];
     __shared__ uint32_t is_last, absorbing_s;
     __shared__ uint8_t wagg[(LONG_FUSED_THREADS / 32) * 32];              // aggregate of every warp's 32 maps
     const uint32_t S = p.def[d].num_states, C = p.def[d].num_classes;
     uint32_t* tr_r = reinterpret_cast<uint32_t*>(long_smem);
-    uint16_t* cls_r = reinterpret_cast<uint16_t*>(tr_r + (size_t)C * P * 32);  // [256][32] class of the byte, one copy per lane (16 KB)
-    uint8_t* maps = reinterpret_cast<uint8_t*>(cls_r + 256 * 32);            // [LONG_FUSED_THREADS][SP]
+    uint32_t* cls_r = tr_r + (size_t)C * P * 32;                             // [256][32]: absolute shared address of (class row of the byte, state 0, lane)
+    uint8_t* maps = reinterpret_cast<uint8_t*>(cls_r + 256 * 32);            // [LONG_FUSED_THREADS][SP], then the staging buffers
     const uint32_t lane = threadIdx.x & 31;
     {
         // the compact tables first (coalesced), then their per-lane copies out of shared memory
@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 4 : 3) long_map
             }
             if (fixed) atomicOr(&absorbing_s, 1u << threadIdx.x);
         }
-        for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) cls_r[i] = staged ? maps[i >> 5] : p.def[d].byte_class[i >> 5];
+        {
+            const uint32_t tr_s0 = (uint32_t)__cvta_generic_to_shared(tr_r);
+            for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x)
+                cls_r[i] = tr_s0 + (uint32_t)(staged ? maps[i >> 5] : p.def[d].byte_class[i >> 5]) * P * 128u + (i & 31u) * 4u;
+        }
         for (uint32_t i = threadIdx.x; i < C * P * 32; i += blockDim.x) {
             const uint32_t e = i >> 5, c = e / P, st = e % P;
             uint32_t nx = S;                                              // trap state: sticky, also the image of every invalid transition
@@ -296,16 +300,20 @@ __global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 4 : 3) long_map
         __syncthreads();
     }
     const uint32_t absorbing = absorbing_s | (1u << S);                   // the trap state is sticky too
-    const uint32_t tr_lane = (uint32_t)__cvta_generic_to_shared(tr_r) + lane * 4;
-    const uint32_t cls_lane = (uint32_t)__cvta_generic_to_shared(cls_r) + lane * 2;
-    const uint32_t rowb = P * 128u;
+    const uint32_t cls_lane = (uint32_t)__cvta_generic_to_shared(cls_r) + lane * 4;
     // the tables are read-only from here on: plain (movable) loads, so that the class rows of a whole vector of bytes are
     // looked up ahead of the dependent chain of state lookups (issue is in order: a class lookup inside the chain would stall it)
     auto lds = [](uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
     // absolute shared address of (class row of `byte`, state 0, this lane)
-    auto row_of = [&](uint32_t byte) { uint32_t k; asm("ld.shared.u16 %0, [%1];" : "=r"(k) : "r"(cls_lane + byte * 64u)); return tr_lane + k * rowb; };
-    // every thread streams through its own half chunk 16 bytes at a time: the loads ask L2 for the whole 128-byte line
-    auto ldv = [](const uint8_t* q) { uint4 v; asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q)); return v; };
+    auto row_of = [&](uint32_t byte) { return lds(cls_lane + byte * 128u); };
+
+    // input staging: the 32 half chunks of a warp are ONE contiguous 16 KB block.  It comes in through shared memory, 64 bytes of
+    // every half chunk at a time, with coalesced 16-byte cp.async (four lanes per row: whole 64-byte pieces of four lines per
+    // instruction instead of 32 different lines); lane l then reads ITS row with conflict-free LDS.128 (row pitch 80 bytes).
+    constexpr uint32_t STAGE = 64, ROWP = STAGE + 16;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(maps + LONG_FUSED_THREADS * SP) + (threadIdx.x >> 5) * (32u * ROWP);
+    auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
+    enum : uint32_t { MODE_ALL = 0, MODE_W0 = 1, MODE_W1 = 2, MODE_W2 = 3, MODE_W4 = 4 };
 
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         // thread = sub-chunk of LONG_SUB bytes (half a chunk: twice the warps for the same chains)
@@ -317,102 +325,122 @@ __global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 4 : 3) long_map
         for (int s = 0; s < SP; s++) st[s] = ((uint32_t)s < S ? (uint32_t)s : S) * 128u;
         uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0, n = SP + 1;
         uint64_t which = 0;
-        if ((uint64_t)k * LONG_SUB < p.len) {
-            const uint64_t a = (uint64_t)k * LONG_SUB;
-            const uint64_t b = a + LONG_SUB < p.len ? a + LONG_SUB : p.len;
-            uint64_t i = a;
-            // ---- all states, 16 bytes per round, until at most 4 distinct images are left --------------------------------------
-            while (i < b) {
-                const uint64_t e = i + 16 < b ? i + 16 : b;
-                if (e - i == 16) {
-                    const uint4 v0 = ldv(p.bytes + i);
-                    const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+        const uint64_t a = (uint64_t)k * LONG_SUB;
+        const uint32_t mylen = a < p.len ? (uint32_t)(p.len - a < LONG_SUB ? p.len - a : LONG_SUB) : 0u;
+        const uint64_t warp_a = (uint64_t)(k & ~31u) * LONG_SUB;           // first byte of the warp's block
+        uint32_t mode = MODE_ALL, wa = 0, wb = 0;
+        int ia = 0, ib = 1;
+
+        // one 16-byte vector (or the last `avail` < 16 bytes of the string) in the lane's current mode
+        auto all_states = [&](const uint4& v, uint32_t avail) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if (avail == 16) {
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        uint32_t rows[4];
+                for (int q = 0; q < 4; q++) {
+                    uint32_t rows[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) rows[j] = row_of((w[q] >> (8 * j)) & 255u);
+                    for (int j = 0; j < 4; j++) rows[j] = row_of((w[q] >> (8 * j)) & 255u);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < 4; j++) {
 #pragma unroll
-                            for (int s = 0; s < SP; s++) st[s] = lds(rows[j] + st[s]);
-                        }
-                    }
-                } else {
-                    for (uint64_t t = i; t < e; t++) {
-                        const uint32_t cabs = row_of((uint32_t)__ldg(p.bytes + t));
-#pragma unroll
-                        for (int s = 0; s < SP; s++) st[s] = lds(cabs + st[s]);
+                        for (int s = 0; s < SP; s++) st[s] = lds(rows[j] + st[s]);
                     }
                 }
-                i = e;
-                n = 0; which = 0;
+            } else {
+                uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3];
+                for (uint32_t t = 0; t < avail; t++) {
+                    const uint32_t cabs = row_of(x0 & 255u);
+                    x0 = __funnelshift_r(x0, x1, 8); x1 = __funnelshift_r(x1, x2, 8); x2 = __funnelshift_r(x2, x3, 8); x3 >>= 8;
 #pragma unroll
-                for (int s = 0; s < SP; s++) {
-                    if ((uint32_t)s >= S) continue;                     // real states only: the trap state maps to itself
-                    const uint32_t v = st[s];
-                    uint32_t j = (n > 0 && v == u0) ? 0u : (n > 1 && v == u1) ? 1u : (n > 2 && v == u2) ? 2u : (n > 3 && v == u3) ? 3u : 4u;
-                    if (j == 4u) {
-                        if (n == 0) u0 = v; else if (n == 1) u1 = v; else if (n == 2) u2 = v; else if (n == 3) u3 = v;
-                        j = n; n++;
-                    }
-                    which |= (uint64_t)(j & 3u) << (2 * s);
+                    for (int s = 0; s < SP; s++) st[s] = lds(cabs + st[s]);
                 }
-                if (n <= 4) break;
             }
-            // ---- the distinct images walk the rest together; an image that is an absorbing state stays where it is ---------------------
-            if (n <= 4 && i < b) {
-                if (n < 4) u3 = S * 128u;
-                if (n < 3) u2 = S * 128u;
-                if (n < 2) u1 = S * 128u;
-                const bool f0 = (absorbing >> (u0 >> 7)) & 1u, f1 = (absorbing >> (u1 >> 7)) & 1u, f2 = (absorbing >> (u2 >> 7)) & 1u, f3 = (absorbing >> (u3 >> 7)) & 1u;
-                const uint32_t moving = (f0 ? 0u : 1u) + (f1 ? 0u : 1u) + (f2 ? 0u : 1u) + (f3 ? 0u : 1u);
-                // the moving images first (a, b; all four when more than two move)
-                uint32_t wa = u0, wb = u1;
-                int ia = 0, ib = 1;
-                if (moving <= 2) {
-                    ia = !f0 ? 0 : !f1 ? 1 : !f2 ? 2 : 3;                  // first moving image (any when none moves)
-                    ib = ia;
-                    if (moving == 2) ib = (!f1 && ia < 1) ? 1 : (!f2 && ia < 2) ? 2 : 3;
-                    wa = ia == 0 ? u0 : ia == 1 ? u1 : ia == 2 ? u2 : u3;
-                    wb = ib == 0 ? u0 : ib == 1 ? u1 : ib == 2 ? u2 : u3;
-                }
-                auto walk_rest = [&](auto width_tag) {
-                    constexpr int W = decltype(width_tag)::value;         // 1, 2: wa (, wb); 4: u0..u3
-                    auto step_row = [&](uint32_t cabs) {
-                        if (W == 4) { u0 = lds(cabs + u0); u1 = lds(cabs + u1); u2 = lds(cabs + u2); u3 = lds(cabs + u3); }
-                        else { wa = lds(cabs + wa); if (W == 2) wb = lds(cabs + wb); }
-                    };
-                    auto step = [&](uint32_t byte) { step_row(row_of(byte)); };
-                    auto step16 = [&](const uint4& v) {
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        uint32_t rows[16];
+            n = 0; which = 0;
 #pragma unroll
-                        for (int q = 0; q < 16; q++) rows[q] = row_of((w[q >> 2] >> (8 * (q & 3))) & 255u);
-#pragma unroll
-                        for (int q = 0; q < 16; q++) step_row(rows[q]);
-                    };
-                    if (i + 64 <= b) {                                    // 64 bytes per round, the next round's vectors in flight
-                        const uint8_t* q = p.bytes + i;
-                        uint4 n0 = ldv(q), n1 = ldv(q + 16), n2 = ldv(q + 32), n3 = ldv(q + 48);
-                        for (; i + 64 <= b; i += 64) {
-                            const uint4 v0 = n0, v1 = n1, v2 = n2, v3 = n3;
-                            if (i + 128 <= b) { q = p.bytes + i + 64; n0 = ldv(q); n1 = ldv(q + 16); n2 = ldv(q + 32); n3 = ldv(q + 48); }
-                            step16(v0); step16(v1); step16(v2); step16(v3);
-                        }
-                    }
-                    for (; i + 16 <= b; i += 16) step16(ldv(p.bytes + i));
-                    for (; i < b; i++) step(__ldg(p.bytes + i));
-                };
-                if (moving > 2) walk_rest(std::integral_constant<int, 4>{});
-                else {
-                    if (moving == 2) walk_rest(std::integral_constant<int, 2>{});
-                    else if (moving == 1) walk_rest(std::integral_constant<int, 1>{});
-                    if (moving >= 1) { if (ia == 0) u0 = wa; else if (ia == 1) u1 = wa; else if (ia == 2) u2 = wa; else u3 = wa; }
-                    if (moving == 2) { if (ib == 1) u1 = wb; else if (ib == 2) u2 = wb; else u3 = wb; }
+            for (int s = 0; s < SP; s++) {
+                if ((uint32_t)s >= S) continue;                         // real states only: the trap state maps to itself
+                const uint32_t x = st[s];
+                uint32_t j = (n > 0 && x == u0) ? 0u : (n > 1 && x == u1) ? 1u : (n > 2 && x == u2) ? 2u : (n > 3 && x == u3) ? 3u : 4u;
+                if (j == 4u) {
+                    if (n == 0) u0 = x; else if (n == 1) u1 = x; else if (n == 2) u2 = x; else if (n == 3) u3 = x;
+                    j = n; n++;
                 }
+                which |= (uint64_t)(j & 3u) << (2 * s);
+            }
+            if (n > 4) return;
+            // at most four distinct images: from here on only those that are not absorbing states walk on
+            if (n < 4) u3 = S * 128u;
+            if (n < 3) u2 = S * 128u;
+            if (n < 2) u1 = S * 128u;
+            const bool f0 = (absorbing >> (u0 >> 7)) & 1u, f1 = (absorbing >> (u1 >> 7)) & 1u, f2 = (absorbing >> (u2 >> 7)) & 1u, f3 = (absorbing >> (u3 >> 7)) & 1u;
+            const uint32_t moving = (f0 ? 0u : 1u) + (f1 ? 0u : 1u) + (f2 ? 0u : 1u) + (f3 ? 0u : 1u);
+            mode = moving == 0 ? MODE_W0 : moving == 1 ? MODE_W1 : moving == 2 ? MODE_W2 : MODE_W4;
+            if (moving == 1 || moving == 2) {
+                ia = !f0 ? 0 : !f1 ? 1 : !f2 ? 2 : 3;
+                ib = ia;
+                if (moving == 2) ib = (!f1 && ia < 1) ? 1 : (!f2 && ia < 2) ? 2 : 3;
+                wa = ia == 0 ? u0 : ia == 1 ? u1 : ia == 2 ? u2 : u3;
+                wb = ib == 0 ? u0 : ib == 1 ? u1 : ib == 2 ? u2 : u3;
+            }
+        };
+        auto walk_vec = [&](auto width_tag, const uint4& v, uint32_t avail) {
+            constexpr int W = decltype(width_tag)::value;                 // 1, 2: wa (, wb); 4: u0..u3
+            auto step_row = [&](uint32_t cabs) {
+                if (W == 4) { u0 = lds(cabs + u0); u1 = lds(cabs + u1); u2 = lds(cabs + u2); u3 = lds(cabs + u3); }
+                else { wa = lds(cabs + wa); if (W == 2) wb = lds(cabs + wb); }
+            };
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if (avail == 16) {
+                uint32_t rows[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) rows[q] = row_of((w[q >> 2] >> (8 * (q & 3))) & 255u);
+#pragma unroll
+                for (int q = 0; q < 16; q++) step_row(rows[q]);
+            } else {
+                uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3];
+                for (uint32_t t = 0; t < avail; t++) {
+                    step_row(row_of(x0 & 255u));
+                    x0 = __funnelshift_r(x0, x1, 8); x1 = __funnelshift_r(x1, x2, 8); x2 = __funnelshift_r(x2, x3, 8); x3 >>= 8;
+                }
+            }
+        };
+
+        if (__any_sync(0xffffffffu, mylen != 0)) {
+#pragma unroll 1
+            for (uint32_t stg = 0; stg < LONG_SUB / STAGE; stg++) {       // warp-uniform: the staging is cooperative
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t row = i * 8 + (lane >> 2), vv = lane & 3u;
+                    const uint64_t g = warp_a + (uint64_t)row * LONG_SUB + stg * STAGE + vv * 16;
+                    const uint32_t left = g < p.len ? (uint32_t)(p.len - g < 16 ? p.len - g : 16) : 0u;   // nothing past the end of the string is read
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(stage_s + row * ROWP + vv * 16), "l"(p.bytes + (left ? g : 0)), "r"(left) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (__all_sync(0xffffffffu, mode == MODE_W1 && mylen >= (stg + 1) * STAGE)) {   // the common case, no per-vector checks
+#pragma unroll
+                    for (uint32_t r = 0; r < STAGE / 16; r++) walk_vec(std::integral_constant<int, 1>{}, lds128(stage_s + lane * ROWP + r * 16), 16u);
+                    __syncwarp();
+                    continue;
+                }
+#pragma unroll 1
+                for (uint32_t r = 0; r < STAGE / 16; r++) {
+                    const uint32_t pos = stg * STAGE + r * 16;
+                    const uint32_t avail = mylen > pos ? (mylen - pos < 16 ? mylen - pos : 16u) : 0u;
+                    if (!avail || mode == MODE_W0) continue;
+                    const uint4 v = lds128(stage_s + lane * ROWP + r * 16);
+                    if (mode == MODE_W1) walk_vec(std::integral_constant<int, 1>{}, v, avail);
+                    else if (mode == MODE_ALL) all_states(v, avail);
+                    else if (mode == MODE_W2) walk_vec(std::integral_constant<int, 2>{}, v, avail);
+                    else walk_vec(std::integral_constant<int, 4>{}, v, avail);
+                }
+                __syncwarp();                                             // everybody is done with the buffer before it is refilled
             }
         }
+        if (mode == MODE_W1 || mode == MODE_W2) { if (ia == 0) u0 = wa; else if (ia == 1) u1 = wa; else if (ia == 2) u2 = wa; else u3 = wa; }
+        if (mode == MODE_W2) { if (ib == 1) u1 = wb; else if (ib == 2) u2 = wb; else u3 = wb; }
+        if (mode == MODE_ALL) n = SP + 1;                                 // never collapsed (or no bytes at all): the vector of all states is the map
         // the chunk's transition vector as state indices (chunks past the end of the string, and an empty string: the identity)
         uint8_t* mine = maps + threadIdx.x * SP;
 #pragma unroll
@@ -500,7 +528,9 @@ __global__ void __launch_bounds__(LONG_GROUP) long_entry_kernel(const __grid_con
     if (k < p.n_chunks) p.def[d].entry[k] = (uint16_t)__ldcg(p.excl + (size_t)k * (LONG_CHUNK / LONG_SUB) * SP + entry_s);   // the prefix in front of its first sub-chunk
 }
 
-static size_t long_fused_smem(uint32_t C, uint32_t P, uint32_t SP) { return (size_t)256 * 64 + (size_t)C * P * 128 + (size_t)LONG_FUSED_THREADS * SP; }
+static size_t long_fused_smem(uint32_t C, uint32_t P, uint32_t SP) {   // tables, class table, maps, one staging buffer per warp
+    return (size_t)256 * 128 + (size_t)C * P * 128 + (size_t)LONG_FUSED_THREADS * SP + (size_t)(LONG_FUSED_THREADS / 32) * 32 * 80;
+}
 static uint32_t long_padded(uint32_t S1) { uint32_t P = 1; while (P < S1) P <<= 1; return P; }
 
 bool long_fused_ok(const LongParams& lp) {
@@ -657,14 +687,15 @@ int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches) 
             const uint32_t SP = S1 <= 16 ? 16u : 32u, P = long_padded(S1);
             const uint32_t n_groups = (lp.n_chunks + LONG_GROUP - 1) / LONG_GROUP, n_supers = (n_groups + LONG_SUPER - 1) / LONG_SUPER;
             const size_t smem = long_fused_smem(lp.def[d].num_classes, P, SP);
-            if (cudaMemsetAsync(lp.super_cnt, 0, (size_t)n_supers * 4, st) != cudaSuccess) { set_error("cudaMemsetAsync(super_cnt)"); return B2R_ERR_CUDA; }
             auto kern = SP == 16 ? long_maps_fused_kernel<16> : long_maps_fused_kernel<32>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("cudaFuncSetAttribute(long_maps_fused_kernel)"); return B2R_ERR_CUDA; }
             // resident CTAs only (equal work per group: a static stride balances): the tables are staged once per CTA
             int per_sm = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)LONG_FUSED_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
             const uint32_t grid = std::min<uint32_t>(n_groups, (uint32_t)(n_sm * per_sm));
-            kern<<<grid, LONG_FUSED_THREADS, smem, st>>>(lp, d, P, n_groups);
+            LongParams q = lp;
+            q.super_cnt = lp.super_cnt + (size_t)d * n_supers;            // zeroed by the caller, one set of counters per def
+            kern<<<grid, LONG_FUSED_THREADS, smem, st>>>(q, d, P, n_groups);
             LAUNCH_CHECK("long_maps_fused_kernel"); (*launches)++;
             const size_t esmem = (size_t)(n_supers + LONG_SUPER) * SP;
             if (esmem > 48 * 1024 && cudaFuncSetAttribute(long_entry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem) != cudaSuccess) { set_error("cudaFuncSetAttribute(long_entry_kernel)"); return B2R_ERR_CUDA; }
@@ -756,7 +787,6 @@ static int launch_long_emit_one(const WalkParams& p, const uint32_t* summary, co
 
 int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(summary2, 0, (size_t)((n_chunks + 1023) / 1024) * 4, st) != cudaSuccess) { set_error("cudaMemsetAsync(summary2)"); return B2R_ERR_CUDA; }
     long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary, summary2);
     LAUNCH_CHECK("long_summary_kernel"); (*launches)++;
     (*launches)++;

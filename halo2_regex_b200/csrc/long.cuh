@@ -50,7 +50,7 @@ struct LongParams {
     uint32_t fused;                      // 1: the fused pass is used (decided by long_plan)
 };
 
-constexpr uint32_t LONG_GROUP = 128;       // chunks per CTA of the fused prefix pass
+constexpr uint32_t LONG_GROUP = 256;       // chunks per CTA of the fused prefix pass (16 warps share one copy of the replicated tables)
 constexpr uint32_t LONG_SUB = 512;         // bytes per thread of the fused prefix pass (a sub-chunk)
 constexpr uint32_t LONG_FUSED_THREADS = LONG_GROUP * (LONG_CHUNK / LONG_SUB);
 constexpr uint32_t LONG_SUPER = 32;        // groups per super group
@@ -60,7 +60,7 @@ bool long_fused_ok(const LongParams& lp);
 
 // host-callable (long.cu)
 int launch_long_prepare(const LongParams& lp, void* stream, uint32_t* launches);
-// summary: one bit per chunk ("has a flagged granule"), followed by summary2: one bit per summary word (zeroed by the caller)
+// summary: one bit per chunk ("has a flagged granule"), summary2: one bit per summary word (zeroed by the caller, as are the super-group counters)
 int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches);
 size_t long_level_nodes(uint32_t n_chunks);   // total nodes over all tree levels
 

@@ -409,6 +409,25 @@ def test_long_string_16_mib_bit_exact():
     assert int(g.mult[0].sum()) == M
 
 
+def test_long_string_64_mib_bit_exact():
+    """BASELINE config 3 at its full size (one 64 MiB string through regex2, 65 536 chunks, 256 groups, 8 super groups) against the
+    oracle, every column; the planted match and a few more straddle chunk, group and super-group boundaries."""
+    import halo2_regex_b200 as H
+    import workloads as W
+    length = 1 << 26
+    body, at = W.config3_numpy(length)
+    plant = np.frombuffer(b" Also for xyzzy.", dtype=np.uint8)
+    for pos in [0, 1013, (1 << 18) - 5, (1 << 23) - 9, (1 << 25) + 1020, length - len(plant)]:
+        body[pos:pos + len(plant)] = plant
+    M = length + 1
+    cfg = product_config("regex2", 64)
+    g, gres = cfg.match_long_host(body, check=False, max_records=16, compact_pitch=128)
+    o, ores = oracle_config("regex2", M).match_batch(body, np.array([0, length], dtype=np.uint64), max_records=16, compact_pitch=128)
+    assert gres.code == ores.code == 0
+    assert H.compare_outputs(g, o) == []
+    assert int(g.mult[0].sum()) == M and int(g.status["n_records"][0]) >= 1
+
+
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("length", [1, 4097, 300000])
 def test_long_string_counter_dfa_never_collapses(length, fused):
