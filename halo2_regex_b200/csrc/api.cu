@@ -516,6 +516,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     WalkParams pw;
     fill_walk_params(c, pw, d_bytes, d_offsets, n_chunks, len, &seg, LONG_CHUNK + 1);
     pw.fuse = 0; pw.prefilled = 0; pw.segment_mode = 1;
+    pw.summary = (uint32_t*)(ws + off_summary); pw.summary2 = (uint32_t*)(ws + off_summary2);   // written by the walk itself (two flag words per chunk)
     pw.fmask = (uint32_t*)(ws + off_fmask);
     for (uint32_t d = 0; d < c->n_defs; d++) {
         if (!pw.def[d].states) pw.def[d].states = ws + off_states[d];
@@ -535,7 +536,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     pe.fmask = pw.fmask;
     for (uint32_t d = 0; d < c->n_defs; d++) pe.def[d].states = pw.def[d].states;
     c->have_last = true;
-    if ((rc = launch_long_emit(pe, wide, pw.fmask, (uint32_t*)(ws + off_summary), (uint32_t*)(ws + off_summary2), n_chunks, chunk_fm_words, st, &c->last_launches))) return rc;
+    if ((rc = launch_long_emit(pe, wide, pw.fm_words <= 2 ? nullptr : pw.fmask, (uint32_t*)(ws + off_summary), (uint32_t*)(ws + off_summary2), n_chunks, chunk_fm_words, st, &c->last_launches))) return rc;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
     rc = enqueue_finalize(c, o, 1, M, st);
     if (rc) return rc;

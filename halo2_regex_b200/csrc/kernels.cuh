@@ -76,6 +76,8 @@ struct WalkParams {
     uint32_t emit_smem_tables;       // 1: emit_kernel stages byte_class / trans in shared memory
     uint32_t segment_mode;           // 1: the "strings" are consecutive chunks of ONE long string (long.cuh): string j starts in
                                      //    init_states[j], stores only its own rows (the last one also the final state), no emit stage
+    uint32_t* summary;               // segment mode: one bit per chunk "has a flagged granule" (one word per tile), and
+    uint32_t* summary2;              //   one bit per summary word (zeroed by the caller); null: not wanted
     uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
     uint32_t prefilled;              // 1: the sparse columns were zeroed before the emit stage runs (long-string path: memset)
     uint32_t spread_fill;            // 1: the fused zero-fill ops are issued across the chunk loop instead of in one burst per tile

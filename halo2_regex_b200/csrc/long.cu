@@ -787,8 +787,10 @@ static int launch_long_emit_one(const WalkParams& p, const uint32_t* summary, co
 
 int launch_long_emit(const WalkParams& p, bool wide, const uint32_t* fmask_chunks, uint32_t* summary, uint32_t* summary2, uint32_t n_chunks, uint32_t chunk_fm_words, void* stream, uint32_t* launches) {
     cudaStream_t st = (cudaStream_t)stream;
-    long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary, summary2);
-    LAUNCH_CHECK("long_summary_kernel"); (*launches)++;
+    if (fmask_chunks) {   // null: the segment walk has written the summary itself
+        long_summary_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(fmask_chunks, chunk_fm_words, n_chunks, summary, summary2);
+        LAUNCH_CHECK("long_summary_kernel"); (*launches)++;
+    }
     (*launches)++;
 #define GO(D_) return wide ? launch_long_emit_one<D_, uint16_t>(p, summary, summary2, n_chunks, chunk_fm_words, st) : launch_long_emit_one<D_, uint8_t>(p, summary, summary2, n_chunks, chunk_fm_words, st)
     switch (p.n_defs) {

@@ -528,6 +528,14 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
             __syncwarp();
         }
+        // long-string path: the flag summary of the ordered emit stage (a tile of 32 chunks is exactly one summary word)
+        if (p.segment_mode && p.summary && p.fm_words <= 2) {
+            const uint32_t word = __ballot_sync(0xffffffffu, valid && (fw0 | fw1) != 0u);
+            if (lane == 0) {
+                p.summary[t64] = word;
+                if (word) atomicOr(p.summary2 + (t64 >> 5), 1u << (t64 & 31u));
+            }
+        }
         // ---- fused emit stage: the tile's states are in L1/L2, its flags and final states in registers --------------------
         if (p.fuse) {
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
