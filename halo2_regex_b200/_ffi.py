@@ -9,7 +9,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(_HERE, "libb2r.so")   # B2R_LIB: an instrumented build of the same library (development aid)
 
 # every symbol include/b2r.h declares (tests check the export list against the header)
 SYMBOLS = """

@@ -80,6 +80,7 @@ void read_env_options(b2r_config* c) {
     if (const char* e = getenv("B2R_DEBUG")) o.debug = (uint32_t)atoi(e);
     if (const char* e = getenv("B2R_SPREAD_FILL")) o.spread_fill = e[0] == '0' ? 0u : 1u;
     if (const char* e = getenv("B2R_FUSE")) o.fuse = e[0] == '0' ? 0u : 1u;
+    if (const char* e = getenv("B2R_STAGGER_NS")) o.stagger_ns = atoi(e);
     if (const char* e = getenv("B2R_SLICES")) o.slices = atoi(e);
     o.trace_host = getenv("B2R_TRACE_HOST") != nullptr;
     if (const char* e = getenv("B2R_HIST_CACHE_LOG2")) o.hist_cache_log2 = atoi(e);
@@ -127,6 +128,9 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     p.debug = c->opt.debug; p.spread_fill = c->opt.spread_fill; p.fuse = c->opt.fuse;
+    // offset warp starts (walk.cuh) pay off for one def on batches of many tiles per warp: config 1 1.444 -> 1.408 ms, config 2 reading (i)
+    // 54.3 -> 56.8 %, the 1023-state DFA 36.5 -> 37 %; three defs lose (35.0 -> 34.2 %), so they keep starting together
+    p.stagger_ns = c->opt.stagger_ns >= 0 ? (uint32_t)c->opt.stagger_ns : (c->n_defs == 1 && p.n_tiles >= 4u * 148u * 16u ? 3u * (uint32_t)max_chars : 0u);
     p.fm_words = (uint32_t)((((max_chars - 1) + 15) / 16 + 31) / 32);
     uint64_t ep = 0;
     for (uint32_t d = 0; d < c->n_defs; d++) ep += 2ull * c->packed[d].num_substrs * c->packed[d].num_states * 4ull;
@@ -515,7 +519,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     seg.row_pitch = LONG_CHUNK;
     WalkParams pw;
     fill_walk_params(c, pw, d_bytes, d_offsets, n_chunks, len, &seg, LONG_CHUNK + 1);
-    pw.fuse = 0; pw.prefilled = 0; pw.segment_mode = 1;
+    pw.fuse = 0; pw.prefilled = 0; pw.segment_mode = 1; pw.stagger_ns = 0;
     pw.summary = (uint32_t*)(ws + off_summary); pw.summary2 = (uint32_t*)(ws + off_summary2);   // written by the walk itself (two flag words per chunk)
     pw.fmask = (uint32_t*)(ws + off_fmask);
     for (uint32_t d = 0; d < c->n_defs; d++) {
@@ -556,6 +560,7 @@ int b2r_config_set_option(b2r_config* c, const char* name, const char* value) {
     else if (!strcmp(name, "debug")) o.debug = (uint32_t)v;
     else if (!strcmp(name, "spread_fill")) o.spread_fill = v ? 1u : 0u;
     else if (!strcmp(name, "fuse")) o.fuse = v ? 1u : 0u;
+    else if (!strcmp(name, "stagger_ns")) o.stagger_ns = v;
     else if (!strcmp(name, "slices")) o.slices = v;
     else if (!strcmp(name, "trace_host")) o.trace_host = v != 0;
     else if (!strcmp(name, "hist_cache_log2")) o.hist_cache_log2 = v;

@@ -130,6 +130,7 @@ struct b2r_config {
         int force_hist_mode = -1;     // smem|global
         uint32_t debug = 0;           // timing experiments only: emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status
         uint32_t spread_fill = 1;
+        int stagger_ns = -1;          // start offset between the warps of a walk CTA (-1 = default, see plan in api.cu)
         uint32_t fuse = 1;            // 0: emit_kernel as its own launch
         int slices = 0;               // host entry point: slices per batch (0 = default)
         bool trace_host = false;

@@ -81,6 +81,7 @@ struct WalkParams {
     uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
     uint32_t prefilled;              // 1: the sparse columns were zeroed before the emit stage runs (long-string path: memset)
     uint32_t spread_fill;            // 1: the fused zero-fill ops are issued across the chunk loop instead of in one burst per tile
+    uint32_t stagger_ns;             // warp w of a CTA starts w * stagger_ns late: the warps' walk and emit phases interleave instead of coinciding
     uint32_t debug;                  // timing experiments only (B2R_DEBUG env): emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status
 };
 

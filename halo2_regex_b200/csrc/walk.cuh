@@ -204,6 +204,14 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zero buffer -> visible to the TMA (async proxy)
     }
     __syncthreads();
+    if (p.stagger_ns && warp) {
+        // every warp has the same period (tile setup, walk, emit stage), so warps that start together stay in phase: all of them
+        // walk (the shared-memory pipe saturates) and then all of them run the emit stage (it idles).  Offset starts keep them apart.
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long until = t0 + (unsigned long long)warp * p.stagger_ns;
+        do { __nanosleep(500); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 < until);
+    }
     TileEmitter<D, ST> emitter(p, etb, lane);
     EmitTotals tot;
 
@@ -265,7 +273,16 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         }
     };
 
+#ifdef B2R_PROBE   // development aid (tools/README): where a warp's time goes, tile by tile; -DB2R_PROBE builds print it per warp
+    auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    const unsigned long long pr_start = gtime();
+    unsigned long long pr_sum[4] = {0, 0, 0, 0};
+    uint32_t pr_tiles = 0;
+#endif
     for (;;) {
+#ifdef B2R_PROBE
+        const unsigned long long pr_t0 = gtime();
+#endif
         unsigned long long t64 = 0;
         if (lane == 0) t64 = atomicAdd(&p.counters->tile_counter, 1ull);
         t64 = __shfl_sync(0xffffffffu, t64, 0);
@@ -366,6 +383,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
         }
 
+#ifdef B2R_PROBE
+        cp_async_wait<0>();
+        const unsigned long long pr_t1 = gtime();
+#endif
         uint32_t fm = 0, fw0 = 0, fw1 = 0;                              // granule flags: current group of 32 granules, words 0 and 1
         uint32_t stash_g = NO_POS;                                      // granule kept in my stash
 #pragma unroll 1
@@ -528,6 +549,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
             __syncwarp();
         }
+#ifdef B2R_PROBE
+        const unsigned long long pr_t2 = gtime();
+#endif
         // long-string path: the flag summary of the ordered emit stage (a tile of 32 chunks is exactly one summary word)
         if (p.segment_mode && p.summary && p.fm_words <= 2) {
             const uint32_t word = __ballot_sync(0xffffffffu, valid && (fw0 | fw1) != 0u);
@@ -541,12 +565,27 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my zero-fill stores have completed ...
             __syncwarp();                                                 // ... and so have those of the other lanes
+#ifdef B2R_PROBE
+            const unsigned long long pr_t3 = gtime();
+#endif
             uint32_t fin[D];
 #pragma unroll
             for (int d = 0; d < D; d++) fin[d] = cur[d] >> NSH;
             emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true, stash_g, stash_s);
+#ifdef B2R_PROBE
+            const unsigned long long pr_t4 = gtime();
+            pr_sum[0] += pr_t1 - pr_t0; pr_sum[1] += pr_t2 - pr_t1; pr_sum[2] += pr_t3 - pr_t2; pr_sum[3] += pr_t4 - pr_t3; pr_tiles++;
+#endif
         }
     }
+#ifdef B2R_PROBE
+    if (lane == 0 && p.n_tiles > 1000) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("probe cta %3d sm %3u warp %2d tiles %2u | us: setup %6.1f walk %7.1f fillwait %6.1f emit %6.1f total %7.1f\n", blockIdx.x, smid, warp, pr_tiles, pr_sum[0] * 1e-3,
+               pr_sum[1] * 1e-3, pr_sum[2] * 1e-3, pr_sum[3] * 1e-3, (gtime() - pr_start) * 1e-3);
+    }
+#endif
     if (p.fuse) emit_publish<D>(p, etb, tot);
 
     // ---- flush the multiplicity bins: bin (s,c) of def d -> dense global histogram [c*S + s] -------------------------------
