@@ -87,6 +87,7 @@ void read_env_options(b2r_config* c) {
     if (const char* e = getenv("B2R_HOST_THREADS")) o.host_threads = atoi(e);
     if (const char* e = getenv("B2R_SMALL_PATH")) o.small_path = atoi(e);
     if (const char* e = getenv("B2R_LONG_FUSED")) o.long_fused = atoi(e);
+    if (const char* e = getenv("B2R_SPARSE_DIRECT")) o.sparse_direct = atoi(e);
 }
 
 }  // namespace
@@ -355,6 +356,7 @@ int b2r_config_new(const b2r_allstr* const* allstr, const b2r_substr* const* con
         CUDA_TRY(cudaStreamCreateWithFlags(&c->pay_stream, cudaStreamNonBlocking));
         for (auto& e : c->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_pay) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaHostAlloc((void**)&c->h_slices, sizeof(BatchCounters) * b2r_config::MAX_SLICES, cudaHostAllocPortable | cudaHostAllocMapped));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -372,7 +374,7 @@ void b2r_config_free(b2r_config* c) {
         cudaFree(c->tables); cudaFree(c->scratch); cudaFree(c->d_batch_status);
         c->ws_fmask.release(); c->ws_long.release();
         for (auto& b : c->ws_states) b.release();
-        c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release(); c->ws_sparse.release();
+        c->ws_bytes.release(); c->ws_offsets.release(); c->ws_cols.release(); c->ws_sparse.release(); c->ws_sparse_arena.release();
         c->pin_sparse[0].release(); c->pin_sparse[1].release(); c->pin_small.release();
         if (c->host_stream) cudaStreamDestroy(c->host_stream);
         if (c->in_stream) cudaStreamDestroy(c->in_stream);
@@ -380,6 +382,7 @@ void b2r_config_free(b2r_config* c) {
         if (c->pay_stream) cudaStreamDestroy(c->pay_stream);
         for (auto& e : c->ev_in) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_done) if (e) cudaEventDestroy(e);
+        for (auto& e : c->ev_pay) if (e) cudaEventDestroy(e);
         if (c->h_slices) cudaFreeHost(c->h_slices);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -567,6 +570,8 @@ int b2r_config_set_option(b2r_config* c, const char* name, const char* value) {
     else if (!strcmp(name, "host_threads")) { o.host_threads = v; c->pool.reset(); }
     else if (!strcmp(name, "small_path")) o.small_path = v;
     else if (!strcmp(name, "sparse_cap")) o.sparse_cap = v;
+    else if (!strcmp(name, "sparse_direct")) o.sparse_direct = v;
+    else if (!strcmp(name, "host_debug")) o.host_debug = v;
     else if (!strcmp(name, "long_fused")) o.long_fused = v;
     else { set_error("unknown option '%s'", name); return B2R_ERR_INVALID_ARG; }
     if (c->multi) return multi_set_option(c->multi, name, value);

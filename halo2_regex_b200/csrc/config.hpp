@@ -74,6 +74,7 @@ public:
     void submit(std::function<void()> fn);
     void wait();                      // until every submitted task has finished
     unsigned size() const { return (unsigned)threads_.size(); }
+    unsigned pending() { std::lock_guard<std::mutex> l(m_); return (unsigned)pending_; }   // tasks submitted and not finished (trace output)
 
 private:
     void run();
@@ -139,6 +140,9 @@ struct b2r_config {
         int small_path = 1;           // 0: small batches take the sliced pipeline too (testing hook)
         int long_fused = 1;           // 0: the long-string path computes the chunk maps with the general multi-kernel pass (testing hook)
         int sparse_cap = 0;           // sparse D2H mode: sectors per column slice before the dense fallback (0 = default; testing hook)
+        int host_debug = 0;           // timing experiments only: 1 = skip the host-side clearing, 2 = skip the host-side scatter (results are wrong)
+        int sparse_direct = 0;        // sparse D2H mode: 1 = the kernel stores the compacted sectors straight into pinned host memory (36-byte
+                                      // PCIe writes); 0 = it compacts into device memory and exact-size copies follow once the host has the count
     } opt;
     b2r::DevBuf ws_fmask;                  // granule flags (walk -> emit)
     b2r::DevBuf ws_long;                   // long-string path: chunk offsets, transition-vector tree, entry states, flag summary
@@ -149,14 +153,14 @@ struct b2r_config {
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before walk, after walk, after emit, after finalize
     // staging for the host-pointer entry points
-    b2r::DevBuf ws_bytes, ws_offsets, ws_cols, ws_sparse;
+    b2r::DevBuf ws_bytes, ws_offsets, ws_cols, ws_sparse, ws_sparse_arena;
     b2r::PinBuf pin_sparse[2], pin_small;
     cudaStream_t host_stream = nullptr;
     cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host entry point: H2D / D2H copies overlapping the kernels
     cudaStream_t pay_stream = nullptr;                        // sparse D2H mode: the compacted sectors of a slice
     b2r::BatchCounters* counters_copy = nullptr;              // small-batch path: finalize_kernel leaves a copy of the batch counters here
     static constexpr int MAX_SLICES = 16;
-    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
+    cudaEvent_t ev_in[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {}, ev_pay[MAX_SLICES] = {};
     b2r::BatchCounters* h_slices = nullptr;    // pinned: the counters of every slice of a host batch
     cudaEvent_t ev_fork = nullptr;
     std::unique_ptr<b2r::HostPool> pool;       // created by the first sparse-mode call

@@ -63,26 +63,67 @@ void HostPool::run() {
 }
 
 // ---- sparse D2H: device-side compaction of a zero-dominated column -----------------------------------------------------------
-// One thread per 32-byte sector of the column slice: non-zero sectors are appended (unordered) as (sector index, 32 bytes).
+// Non-zero 32-byte sectors of the column slice are appended as (sector index, 32 bytes).  A CTA takes 4096 consecutive sectors at
+// a time, counts its non-zero ones, reserves their places with ONE atomic and writes them in ascending sector order: the host
+// threads that scatter the list into the caller's dense column (and clear it again before the next call) then walk through memory
+// in long ascending runs instead of jumping at random (page-table walks and DRAM row misses were most of their time).
 // `count` keeps counting past `cap`: the host sees the overflow and copies that column slice densely instead.
+constexpr int SPARSIFY_K = 16;           // sectors per thread and pass
 __global__ void __launch_bounds__(256) sparsify_kernel(const uint4* __restrict__ col, uint64_t n_sectors, uint32_t* __restrict__ idx, uint4* __restrict__ payload,
                                                        uint32_t cap, unsigned int* count) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const unsigned lane = threadIdx.x & 31;
-    const uint64_t n_round = (n_sectors + 31) & ~uint64_t(31);             // whole warps stay in the loop (ballot)
-    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += stride) {
-        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-        if (s < n_sectors) { a = __ldcs(col + 2 * s); b = __ldcs(col + 2 * s + 1); }
-        const bool nz = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, nz);
-        if (!m) continue;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(count, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (nz) {
-            const unsigned k = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-            if (k < cap) { idx[k] = (uint32_t)s; payload[2 * (size_t)k] = a; payload[2 * (size_t)k + 1] = b; }
+    __shared__ uint32_t s_cnt[SPARSIFY_K * 8];                             // non-zero sectors of (row j, warp w), then their exclusive prefix
+    __shared__ uint32_t s_wsum[4], s_base;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint64_t PER_CTA = 256 * SPARSIFY_K;
+    for (uint64_t b0 = (uint64_t)blockIdx.x * PER_CTA; b0 < n_sectors; b0 += (uint64_t)gridDim.x * PER_CTA) {
+        uint32_t mine = 0;                                                 // bit j: my sector of row j is non-zero
+#pragma unroll
+        for (int j = 0; j < SPARSIFY_K; j++) {
+            const uint64_t s = b0 + (uint64_t)j * 256 + threadIdx.x;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (s < n_sectors) { a = __ldcg(col + 2 * s); b = __ldcg(col + 2 * s + 1); }
+            const bool nz = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, nz);
+            if (nz) mine |= 1u << j;
+            if (lane == 0) s_cnt[j * 8 + warp] = (uint32_t)__popc(m);
         }
+        __syncthreads();
+        // exclusive prefix over the SPARSIFY_K * 8 = 128 counts, in (row, warp) order = ascending sector order
+        uint32_t v = 0, incl = 0;
+        if (threadIdx.x < SPARSIFY_K * 8) {
+            v = s_cnt[threadIdx.x];
+            incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+            if (lane == 31) s_wsum[warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < SPARSIFY_K * 8) {
+            uint32_t before = 0;
+            for (unsigned w = 0; w < warp; w++) before += s_wsum[w];
+            s_cnt[threadIdx.x] = before + incl - v;
+            if (threadIdx.x == SPARSIFY_K * 8 - 1) {
+                const uint32_t total = before + incl;
+                s_base = total ? atomicAdd(count, total) : 0u;
+            }
+        }
+        __syncthreads();
+        if (__any_sync(0xffffffffu, mine != 0)) {
+            const uint32_t base = s_base;
+#pragma unroll 1
+            for (int j = 0; j < SPARSIFY_K; j++) {
+                const bool nz = (mine >> j) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, nz);
+                if (!nz) continue;
+                const uint32_t k = base + s_cnt[j * 8 + warp] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (k < cap) {
+                    const uint64_t s = b0 + (uint64_t)j * 256 + threadIdx.x;
+                    idx[k] = (uint32_t)s;
+                    payload[2 * (size_t)k] = __ldcg(col + 2 * s); payload[2 * (size_t)k + 1] = __ldcg(col + 2 * s + 1);   // the second read hits L2
+                }
+            }
+        }
+        __syncthreads();                                                   // s_cnt / s_base are reused by the next pass
     }
 }
 
@@ -110,9 +151,10 @@ unsigned default_host_threads() {
     if (!hw) hw = 4;
     unsigned share = 1;                // ranks of a torchrun job share the host cores
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) share = (unsigned)v; }
-    // half the cores, at most 8: more threads take memory bandwidth from the DMA engines (2^20 x 1 KiB strings, 16-core host:
-    // 40.5 ms per call with 4 threads, 35.9 with 8, 36.4 with 12, 39.6 with 16)
-    return std::max(2u, std::min(8u, hw / 2 / share));
+    // three quarters of the cores, at most 12.  Clearing and scattering one 32-byte sector is one cache miss; a core keeps about a
+    // dozen in flight, so the sector rate grows with the threads until they take memory bandwidth from the DMA engines
+    // (2^20 x 1 KiB strings, 16-core host, staged sparse mode: 33.9 ms per call with 8 threads, 33.0 with 12; 16 is slower)
+    return std::max(2u, std::min(12u, hw * 3 / 4 / share));
 }
 
 struct SparseCol {                     // one zero-dominated column of a host batch
@@ -342,6 +384,7 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
         arena = c->sparse_memo.arena ^ 1;
         if ((rc = c->ws_sparse.reserve(n_sc * n_slices * sizeof(unsigned int) + 256))) return rc;
         if ((rc = c->pin_sparse[arena].reserve(sp_need + 256))) return rc;
+        if (!c->opt.sparse_direct && (rc = c->ws_sparse_arena.reserve(sp_need + 256))) return rc;
         if (!c->pool) c->pool.reset(new HostPool(c->opt.host_threads > 0 ? (unsigned)c->opt.host_threads : default_host_threads()));
         CUDA_TRY(cudaMemsetAsync(c->ws_sparse.p, 0, n_sc * n_slices * sizeof(unsigned int), st));
         // B2R_OUT_SPARSE_REUSE: these are the buffers the previous call filled (same batch geometry, hence the same arena layout):
@@ -351,7 +394,8 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
                 memo.sparse_cap == c->opt.sparse_cap && memo.hosts.size() == n_sc && c->pin_sparse[memo.arena].p;
         for (size_t k = 0; reuse && k < n_sc; k++) reuse = memo.hosts[k] == scols[k]->host;
         memo.valid = false;                                               // until this call has completed
-        if (reuse) {
+        if (reuse && (c->opt.host_debug & 1)) {
+        } else if (reuse) {
             const uint32_t piece = 1u << 16;
             for (int i = 0; i < n_slices; i++)
                 for (size_t k = 0; k < n_sc; k++) {
@@ -364,7 +408,8 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
                     for (uint32_t e0 = 0; e0 < cnt; e0 += piece)
                         c->pool->submit([=] {
                             const uint32_t e1 = std::min(cnt, e0 + piece);
-                            for (uint32_t e = e0; e < e1; e++) {   // one cache miss per sector: keep a dozen in flight
+                            for (uint32_t e = e0; e < e1; e++) {   // one cache miss per sector: a dozen in flight towards L1, more towards L2
+                                if (e + 48 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 48] * 32, 0, 1);
                                 if (e + 12 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 12] * 32, 1, 0);
                                 const uint64_t o = (uint64_t)idx[e] * 32;
                                 memset(dst + o, 0, (size_t)std::min<uint64_t>(32, bytes - o));
@@ -382,6 +427,11 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
     }
     unsigned int* const d_cnt = (unsigned int*)c->ws_sparse.p;
     unsigned char* const sp_host = (unsigned char*)c->pin_sparse[arena].p;   // unified addressing: the kernels write through the same pointer
+    // where sparsify_kernel writes.  Direct mode: pinned host memory, i.e. one PCIe write per 4-byte index and per 32-byte sector
+    // (a transaction header for every 32 bytes: 0.25 GB of sectors occupied the link like 0.6 GB).  Staged mode (default): a device
+    // arena of the same layout; the host learns the count (published below), then exact-size copies bring index list and sectors over
+    const bool staged = sparse && n_sc && !c->opt.sparse_direct;
+    unsigned char* const sp_dev = staged ? (unsigned char*)c->ws_sparse_arena.p : sp_host;
 
     const bool trace = c->opt.trace_host;                                 // timing aid: where the copies sit on the time line
     const auto wall0 = std::chrono::steady_clock::now();
@@ -428,9 +478,9 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
         if (sparse && ni)
             for (size_t k = 0; k < n_sc; k++) {
                 const SliceCol& s = sc[i * n_sc + k];
-                const unsigned grid = (unsigned)std::min<uint64_t>((s.n_sectors + 255) / 256, (uint64_t)n_sm * 8);
-                sparsify_kernel<<<grid, 256, 0, st>>>((const uint4*)(cb + scols[k]->off + lo * scols[k]->stride), s.n_sectors, (uint32_t*)(sp_host + s.idx_off),
-                                                      (uint4*)(sp_host + s.pay_off), s.cap, d_cnt + i * n_sc + k);
+                const unsigned grid = (unsigned)std::min<uint64_t>((s.n_sectors + 256 * SPARSIFY_K - 1) / (256 * SPARSIFY_K), (uint64_t)n_sm * 8);
+                sparsify_kernel<<<grid, 256, 0, st>>>((const uint4*)(cb + scols[k]->off + lo * scols[k]->stride), s.n_sectors, (uint32_t*)(sp_dev + s.idx_off),
+                                                      (uint4*)(sp_dev + s.pay_off), s.cap, d_cnt + i * n_sc + k);
                 CUDA_TRY(cudaGetLastError());
             }
         if (sparse && n_sc) {
@@ -438,9 +488,13 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
             CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(c->ev_done[i], st));
+        if (trace && i == n_slices - 1) CUDA_TRY(cudaEventRecord(tev[1], c->in_stream));
+        // staged sparse mode: the D2H copies of a slice are issued further down, by the loop that has waited for its kernels — the
+        // copy engine serves copies in the order they were issued, and the (small) compacted sectors of slice i have to go in FRONT of
+        // the state column of slice i, not behind the state columns of every slice (the host threads scatter while the big copies run)
+        if (staged) continue;
         CUDA_TRY(cudaStreamWaitEvent(c->out_stream, c->ev_done[i], 0));
         if (trace && i == 0) CUDA_TRY(cudaEventRecord(tev[2], c->out_stream));
-        if (trace && i == n_slices - 1) CUDA_TRY(cudaEventRecord(tev[1], c->in_stream));
         for (const Copy& cp : copies)
             if (cp.stride && cp.pinned && !cp.sparse && ni) {
                 CUDA_TRY(cudaMemcpyAsync((unsigned char*)cp.host + lo * cp.stride, cb + cp.off + lo * cp.stride, ni * cp.stride, cudaMemcpyDeviceToHost, c->out_stream));
@@ -458,27 +512,19 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
         const unsigned int* h_cnt = (const unsigned int*)(sp_host + cnt_off);
         std::vector<char> dense(n_sc * n_slices, 0);
         w_pay = wall_ms();
-        c->pool->wait();                                                  // the zeros are in place (reused buffers: the old sectors are cleared)
-        w_zero = wall_ms();
+        bool cleared = false;
         bool any_dense = false;
-        for (int i = 0; i < n_slices; i++) {
+        // the scatter jobs of slice i: its compacted sectors are in the pinned arena (staged mode: once ev_pay[i] has fired)
+        auto scatter_slice = [&](int i) {
+            // every zero is in place first (reused buffers: the old sectors are cleared): a clear and a scatter may hit the same sector
+            if (!cleared) { c->pool->wait(); w_zero = wall_ms(); cleared = true; }
             const uint64_t lo = slice_lo[i], ni = cut(i + 1) - lo;
-            CUDA_TRY(cudaEventSynchronize(c->ev_done[i]));
-            d2h += n_sc * 4;
+            if (c->opt.host_debug & 2) return;
             for (size_t k = 0; k < n_sc && ni; k++) {
                 const SliceCol& s = sc[i * n_sc + k];
                 const uint32_t cnt = h_cnt[i * n_sc + k];
+                if (!cnt || dense[i * n_sc + k]) continue;
                 unsigned char* dst = (unsigned char*)scols[k]->host + lo * scols[k]->stride;
-                if (cnt > s.cap) {   // not sparse after all: this column slice crosses densely
-                    dense[i * n_sc + k] = 1;
-                    if (!any_dense) CUDA_TRY(cudaStreamWaitEvent(c->pay_stream, c->ev_done[i], 0));
-                    any_dense = true;
-                    CUDA_TRY(cudaMemcpyAsync(dst, cb + scols[k]->off + lo * scols[k]->stride, s.bytes, cudaMemcpyDeviceToHost, c->pay_stream));
-                    d2h += s.bytes;
-                    continue;
-                }
-                if (!cnt) continue;
-                d2h += (size_t)cnt * 36;
                 const uint32_t* idx = (const uint32_t*)(sp_host + s.idx_off);
                 const unsigned char* pay = sp_host + s.pay_off;
                 const uint64_t bytes = s.bytes;
@@ -487,14 +533,57 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
                     c->pool->submit([=] {
                         const uint32_t e1 = std::min(cnt, e0 + piece);
                         for (uint32_t e = e0; e < e1; e++) {
+                            if (e + 48 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 48] * 32, 0, 1);
                             if (e + 12 < e1) __builtin_prefetch(dst + (uint64_t)idx[e + 12] * 32, 1, 0);
                             const uint64_t o = (uint64_t)idx[e] * 32;
                             memcpy(dst + o, pay + (size_t)e * 32, (size_t)std::min<uint64_t>(32, bytes - o));
                         }
                     });
             }
+        };
+        for (int i = 0; i < n_slices; i++) {
+            const uint64_t lo = slice_lo[i], ni = cut(i + 1) - lo;
+            CUDA_TRY(cudaEventSynchronize(c->ev_done[i]));
+            if (trace) fprintf(stderr, "[b2r]   slice %2d: kernels done %.2f ms", i, wall_ms());
+            d2h += n_sc * 4;
+            // the host has waited for the slice's kernels, so its copies need no event; staged mode: everything on out_stream, in the
+            // order payload -> ev_pay -> dense columns; direct mode: only a dense fallback is copied (pay_stream)
+            cudaStream_t ps = staged ? c->out_stream : c->pay_stream;
+            bool waited = staged;
+            auto pay_wait = [&]() -> int { if (!waited) { CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_done[i], 0)); waited = true; } return 0; };
+            if (staged && trace && i == 0) CUDA_TRY(cudaEventRecord(tev[2], c->out_stream));
+            for (size_t k = 0; k < n_sc && ni; k++) {
+                const SliceCol& s = sc[i * n_sc + k];
+                const uint32_t cnt = h_cnt[i * n_sc + k];
+                unsigned char* dst = (unsigned char*)scols[k]->host + lo * scols[k]->stride;
+                if (cnt > s.cap) {   // not sparse after all: this column slice crosses densely
+                    dense[i * n_sc + k] = 1;
+                    if ((rc = pay_wait())) return rc;
+                    any_dense = true;
+                    CUDA_TRY(cudaMemcpyAsync(dst, cb + scols[k]->off + lo * scols[k]->stride, s.bytes, cudaMemcpyDeviceToHost, ps));
+                    d2h += s.bytes;
+                    continue;
+                }
+                if (!cnt) continue;
+                d2h += (size_t)cnt * 36;
+                if (staged) {
+                    CUDA_TRY(cudaMemcpyAsync(sp_host + s.idx_off, sp_dev + s.idx_off, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ps));
+                    CUDA_TRY(cudaMemcpyAsync(sp_host + s.pay_off, sp_dev + s.pay_off, (size_t)cnt * 32, cudaMemcpyDeviceToHost, ps));
+                }
+            }
+            if (staged) {   // scatter one slice behind the copies
+                CUDA_TRY(cudaEventRecord(c->ev_pay[i], ps));
+                for (const Copy& cp : copies)
+                    if (cp.stride && cp.pinned && !cp.sparse && ni) {
+                        CUDA_TRY(cudaMemcpyAsync((unsigned char*)cp.host + lo * cp.stride, cb + cp.off + lo * cp.stride, ni * cp.stride, cudaMemcpyDeviceToHost, ps));
+                        d2h += ni * cp.stride;
+                    }
+                if (i > 0) { CUDA_TRY(cudaEventSynchronize(c->ev_pay[i - 1])); scatter_slice(i - 1); }
+            } else scatter_slice(i);
+            if (trace) fprintf(stderr, ", sectors of slice %d in host memory %.2f ms, scatter jobs pending %u\n", i - 1, wall_ms(), c->pool->pending());
         }
-        if (any_dense) CUDA_TRY(cudaStreamSynchronize(c->pay_stream));
+        if (staged) { CUDA_TRY(cudaEventSynchronize(c->ev_pay[n_slices - 1])); scatter_slice(n_slices - 1); }
+        if (any_dense && !staged) CUDA_TRY(cudaStreamSynchronize(c->pay_stream));
         c->pool->wait();
         w_scat = wall_ms();
         SparseMemo& memo = c->sparse_memo;                                // what the next B2R_OUT_SPARSE_REUSE call has to clear
