@@ -358,13 +358,29 @@ def long_leg(ctx, H, W, steps, warmup):
     algo_bytes = length + out.written_bytes()
     st = ctx.stream()
 
-    def step():
-        cfg.match_long_device(d, out, stream=st)
+    def enqueue():
+        cfg.match_long_device(d, out, stream=torch.cuda.current_stream(dev))
 
     for _ in range(warmup):
-        step()
+        enqueue()
     assert cfg.batch_result(stream=st).code == 0
     launches = cfg.last_launch_count()
+    # the step (five kernels, the memset nodes of the sparse columns on a side branch) as ONE CUDA graph, like the batch path
+    graph = None
+    if not ctx.args.no_graph:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture of the long-string step failed ({e!r}); timing plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    step = graph.replay if graph is not None else enqueue
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     torch.cuda.synchronize()
     for i in range(steps):
@@ -389,7 +405,7 @@ def long_leg(ctx, H, W, steps, warmup):
     return {"workload": f"ONE {length >> 20} MiB string through regex2_test + substr2 (chunked parallel-prefix composition of the transition vectors), "
                         f"` Also for xyz.` planted at offset {at}; M = len + 1 (BASELINE configs[3]); rank 0 only",
             "string_len": length, "max_chars_size": m, "defs": 1, "states": [13], "value": length / (ms_step * 1e-3) / 1e9, "unit": UNIT, "steps": steps,
-            "ms_per_step": ms_step, "step_ms_min": ms[0], "kernels_per_step": launches, "algorithmic_bytes_per_launch": algo_bytes,
+            "ms_per_step": ms_step, "step_ms_min": ms[0], "kernels_per_step": launches, "cuda_graph": graph is not None, "algorithmic_bytes_per_launch": algo_bytes,
             "achieved_gbs": achieved, "frac": achieved / ctx.peak, "frac_note": "whole step (every launch of the path), not one kernel",
             "parity": {"oracle_whole_string_bit_exact": ok, "mult_sum_equals_rows": mult_ok}}
 

@@ -481,8 +481,8 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     if ((rc = c->ws_long.reserve(need))) return rc;
     unsigned char* ws = (unsigned char*)c->ws_long.p;
     uint64_t* d_offsets = (uint64_t*)(ws + off_offsets);
-    const uint64_t whole[2] = {0, len};
-    CUDA_TRY(cudaMemcpyAsync(d_offsets + n_chunks + 1, whole, sizeof whole, cudaMemcpyHostToDevice, st));
+    // (the {0, len} pair of the whole string behind the chunk offsets is written by the kernel that writes those: no host copy on this
+    // path, so a caller may capture it in a CUDA graph)
 
     // ---- 1 + 2: transition vectors of the chunks, composition tree, entry state of every chunk ------------------------------
     LongParams lp;

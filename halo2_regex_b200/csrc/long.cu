@@ -14,6 +14,7 @@ namespace b2r {
 __global__ void long_offsets_kernel(uint64_t* offsets, uint32_t n_chunks, uint64_t len) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n_chunks) { const uint64_t o = (uint64_t)i * LONG_CHUNK; offsets[i] = o < len ? o : len; }
+    if (i == 0) { offsets[n_chunks + 1] = 0; offsets[n_chunks + 2] = len; }   // the {0, len} pair of the whole string (emit stage)
 }
 
 // f_k[s] for every chunk k and state s in [0, S]; S is the trap state (an invalid transition, sticky).
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(LONG_FUSED_THREADS, SP == 16 ? 2 : 1) long_map
         // thread = sub-chunk of LONG_SUB bytes (half a chunk: twice the warps for the same chains)
         const uint32_t k = grp * LONG_FUSED_THREADS + threadIdx.x;
         if ((k & 1u) == 0 && (k >> 1) < p.n_chunks) p.offsets[k >> 1] = (uint64_t)(k >> 1) * LONG_CHUNK;   // chunk offsets for the walk kernel
-        if (k == 0) p.offsets[p.n_chunks] = p.len;
+        if (k == 0) { p.offsets[p.n_chunks] = p.len; p.offsets[p.n_chunks + 1] = 0; p.offsets[p.n_chunks + 2] = p.len; }   // + the {0, len} pair of the whole string
         uint32_t st[SP];
 #pragma unroll
         for (int s = 0; s < SP; s++) st[s] = ((uint32_t)s < S ? (uint32_t)s : S) * 128u;
