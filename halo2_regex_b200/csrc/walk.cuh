@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char dsmem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+#ifdef B2R_PROBE
+    unsigned long long pr_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_entry));
+#endif
 
     const WalkLayout lay = walk_layout(p, SB);
     const uint32_t base_s = (smem_u32(dsmem) + lay.align - 1) & ~(lay.align - 1);
@@ -579,12 +583,13 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         }
     }
 #ifdef B2R_PROBE
-    if (lane == 0 && p.n_tiles > 1000) {
+    if (lane == 0 && (blockIdx.x % 37) == 0 && p.n_tiles > 1000) {   // four CTAs: printing from every warp would stretch the kernel
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        printf("probe cta %3d sm %3u warp %2d tiles %2u | us: setup %6.1f walk %7.1f fillwait %6.1f emit %6.1f total %7.1f\n", blockIdx.x, smid, warp, pr_tiles, pr_sum[0] * 1e-3,
-               pr_sum[1] * 1e-3, pr_sum[2] * 1e-3, pr_sum[3] * 1e-3, (gtime() - pr_start) * 1e-3);
+        printf("probe cta %3d sm %3u warp %2d tiles %2u | us: prologue %5.1f setup %6.1f walk %7.1f fillwait %6.1f emit %6.1f loop %7.1f\n", blockIdx.x, smid, warp, pr_tiles,
+               (pr_start - pr_entry) * 1e-3, pr_sum[0] * 1e-3, pr_sum[1] * 1e-3, pr_sum[2] * 1e-3, pr_sum[3] * 1e-3, (gtime() - pr_start) * 1e-3);
     }
+    const unsigned long long pr_loop_end = gtime();
 #endif
     if (p.fuse) emit_publish<D>(p, etb, tot);
 
@@ -612,6 +617,12 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
         }
     }
+#ifdef B2R_PROBE
+    __syncthreads();
+    if (threadIdx.x == 0 && (blockIdx.x % 37) == 0 && p.n_tiles > 1000)
+        printf("probe cta %3d: kernel entry -> tile loop %.1f us, epilogue (publish + bin flush, after the slowest warp of the CTA) %.1f us, entry -> exit %.1f us\n", blockIdx.x,
+               (pr_start - pr_entry) * 1e-3, (gtime() - pr_loop_end) * 1e-3, (gtime() - pr_entry) * 1e-3);
+#endif
 }
 
 }  // namespace b2r
