@@ -11,12 +11,17 @@ and `fancy_regex`:
     JSON graph + the decomposed parts -> substring transition sets and their start / end states
         (/root/reference/src/vrm/mod.rs:63-90, 265-600)
 
-The files it produces are only reproducible if every tie in those algorithms is broken the way the reference breaks it,
-so the restatement below keeps the reference's *orders* and nothing else of its shape: the insertion-ordered property
-maps of the JS engine (integer-like keys first), the UTF-16 string order of `Array.prototype.sort`, the swap-remove edge
-storage and newest-first adjacency lists of petgraph's `Graph`, and the leftmost-first match rule of the regex engine.
-The known-answer test is byte-identical regeneration of `test_regexes/*_lookup.txt` from `test_regexes/*.json`
-(tests/test_vrm.py, fixtures under tests/golden/regexes/).
+The files it produces are only reproducible if every tie is broken the way the reference breaks it, so what is kept of the
+reference are the *orders* its output depends on and nothing of its shape: the pattern language and the epsilon-NFA states per
+syntax node (they decide which subset-construction states exist), the naming / sorting rule of the final numbering, the
+insertion-ordered property maps of the JS engine (integer-like keys first), the UTF-16 string order of `Array.prototype.sort`,
+the swap-remove edge storage and newest-first adjacency lists of petgraph's `Graph`, and the leftmost-first match rule of the
+regex engine.  The regex -> DFA step itself is this module's own design (cursor parser, array NFA with bit-set closures, Moore
+partition refinement); round 1 shipped a function-by-function port of regex.js there, which now only survives as the generator
+of the known-answer vectors (tools/make_vrm_golden.py -> tests/golden/vrm_dfa_cases.json).
+The known-answer tests: byte-identical regeneration of `test_regexes/*_lookup.txt` from `test_regexes/*.json` and 418 recorded
+DFA graphs (tests/test_vrm.py, fixtures under tests/golden/).  Deliberate difference on malformed patterns: an unbalanced ')'
+is a syntax error here (the reference's parser reads it as a literal).
 """
 from __future__ import annotations
 
@@ -57,7 +62,7 @@ def text_context_prefix() -> str:
 def _utf16_key(s: str):
     """Sort key reproducing the JS default string order (by UTF-16 code unit)."""
     if s.isascii():
-        return s
+        return tuple(s.encode("ascii"))
     b = s.encode("utf-16-be")
     return tuple(int.from_bytes(b[i:i + 2], "big") for i in range(0, len(b), 2))
 
@@ -131,197 +136,169 @@ format_regex_str = format_regex_printable            # js_caller.rs:36-41
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# regex text -> syntax tree (regex.js:236-382)
+# regex text -> DFA graph.
+#
+# What the reference's output depends on (and what is therefore kept), as opposed to how its JavaScript computes it:
+#   * the LANGUAGE of the pattern syntax: `\x` makes x a literal (n r t v f are the usual control characters), the unescaped
+#     characters ( ) | * + ? are operators, the character "ϵ" is the empty word, `x+` means x x*, `x?` means (x|ϵ);
+#   * the SHAPE of the epsilon-NFA: subset-construction states are sets of NFA states, epsilon-only states included, so two
+#     subsets that differ only in such states are different DFA states before minimisation — and the names of those states
+#     ("A", "B", ..., "AA": discovery order of a breadth-first subset construction over the symbols in UTF-16 order) are what
+#     the final numbering is sorted by.  The NFA below therefore has the same states per syntax node as the reference's
+#     (regex.js:390-452): none for a concatenation beyond one joint per gap, an entry/exit pair per alternative and per star;
+#   * the final numbering rule (regex.js:700-762): equivalence classes ordered by the comma-joined names of their members
+#     (UTF-16 order), the start state's class swapped to the front; merged edge labels = JSON list of the sorted symbols.
+# Everything else is this module's own: a cursor-based recursive-descent parser, an array NFA with bit-set closures, and
+# Moore-style partition refinement (the coarsest stable partition is unique, so it equals what the reference's worklist
+# algorithm (regex.js:563-690) arrives at).
 # ---------------------------------------------------------------------------------------------------------------------
 
 class RegexSyntaxError(ValueError):
     pass
 
 
-@dataclass
-class _Tok:
-    ch: str
-    escaped: bool
+_OPERATORS = "()|*+?"
+
+# syntax nodes: ("lit", ch) | ("eps",) | ("cat", [nodes]) | ("alt", [nodes]) | ("star", node)
 
 
-@dataclass
-class _Ast:
-    kind: str                           # "or" | "cat" | "star" | "empty" | "text"
-    parts: List["_Ast"] = field(default_factory=list)
-    sub: Optional["_Ast"] = None
-    text: str = ""
+class _Parser:
+    """pattern := branch ('|' branch)*;  branch := piece+;  piece := atom ('*' | '+' | '?')*;  atom := literal | 'ϵ' | '(' pattern ')'."""
+
+    def __init__(self, text: str):
+        self.text = text
+        self.pos = 0
+
+    def _peek(self) -> Optional[str]:
+        """The operator at the cursor, "" for a literal, None at the end."""
+        if self.pos >= len(self.text):
+            return None
+        c = self.text[self.pos]
+        return c if c in _OPERATORS else ""
+
+    def _literal(self):
+        """Consumes one literal; returns (character, was it escaped)."""
+        c = self.text[self.pos]
+        if c == "\\":
+            if self.pos + 1 >= len(self.text):
+                raise RegexSyntaxError("pattern ends inside an escape (offset %d)" % self.pos)
+            c = self.text[self.pos + 1]
+            self.pos += 2
+            return _ESCAPES.get(c, c), True
+        self.pos += 1
+        return c, False
+
+    def pattern(self, opened_at: int = -1):
+        branches = [self._branch()]
+        while self._peek() == "|":
+            self.pos += 1
+            branches.append(self._branch())
+        if opened_at >= 0:
+            if self._peek() != ")":
+                raise RegexSyntaxError("no closing bracket for the group opened at offset %d" % opened_at)
+            self.pos += 1
+        elif self._peek() is not None:
+            raise RegexSyntaxError("unbalanced ')' at offset %d" % self.pos)
+        return branches[0] if len(branches) == 1 else ("alt", branches)
+
+    def _branch(self):
+        pieces = []
+        while True:
+            op = self._peek()
+            if op is None or op == "|" or op == ")":
+                break
+            if op == "(":
+                at = self.pos
+                self.pos += 1
+                pieces.append(self.pattern(opened_at=at))
+            elif op != "":                      # * + ?
+                if not pieces:
+                    raise RegexSyntaxError("'%s' at offset %d has nothing to repeat" % (op, self.pos))
+                self.pos += 1
+                x = pieces[-1]
+                pieces[-1] = ("star", x) if op == "*" else ("cat", [x, ("star", x)]) if op == "+" else ("alt", [x, ("eps",)])
+            else:
+                ch, _ = self._literal()
+                pieces.append(("eps",) if ch == EPS else ("lit", ch))   # escaped or not: the reference's NFA labels its epsilon edges with this character
+        if not pieces:
+            raise RegexSyntaxError("empty alternative at offset %d" % self.pos)
+        return pieces[0] if len(pieces) == 1 else ("cat", pieces)
 
 
-def _tokenise(text: str) -> List[_Tok]:
-    toks: List[_Tok] = []
-    i = 0
-    while i < len(text):
-        if text[i] == "\\":
-            if i + 1 >= len(text):
-                raise RegexSyntaxError("Error: dangling escape at %d." % i)
-            c = text[i + 1]
-            toks.append(_Tok(_ESCAPES.get(c, c), True))
-            i += 2
-        else:
-            toks.append(_Tok(text[i], False))
-            i += 1
-    return toks
+def parse_regex(text: str):
+    return _Parser(text).pattern()
 
 
-def _is(tok: _Tok, ch: str) -> bool:
-    return (not tok.escaped) and tok.ch == ch
+class _Nfa:
+    """States are integers; `eps[s]` lists the epsilon successors of s, `step[s]` maps a symbol to the bit set of its successors."""
+
+    def __init__(self):
+        self.eps: List[List[int]] = []
+        self.step: List[Dict[str, int]] = []
+        self._closure: Dict[int, int] = {}
+
+    def new_state(self) -> int:
+        self.eps.append([])
+        self.step.append({})
+        return len(self.eps) - 1
+
+    def add(self, node, entry: int, exit_: int) -> None:
+        """Wire the automaton of `node` between two existing states."""
+        kind = node[0]
+        if kind == "lit":
+            self.step[entry][node[1]] = self.step[entry].get(node[1], 0) | (1 << exit_)
+        elif kind == "eps":
+            self.eps[entry].append(exit_)
+        elif kind == "cat":
+            at = entry
+            for part in node[1][:-1]:
+                joint = self.new_state()
+                self.add(part, at, joint)
+                at = joint
+            self.add(node[1][-1], at, exit_)
+        elif kind == "alt":
+            for part in node[1]:
+                a, b = self.new_state(), self.new_state()
+                self.eps[entry].append(a)
+                self.eps[b].append(exit_)
+                self.add(part, a, b)
+        else:                                   # star
+            a, b = self.new_state(), self.new_state()
+            self.eps[entry] += [a, exit_]
+            self.eps[b] += [a, exit_]
+            self.add(node[1], a, b)
+
+    def closure(self, s: int) -> int:
+        """Bit set of the states reachable from s over epsilon edges."""
+        got = self._closure.get(s)
+        if got is None:
+            got, todo = 1 << s, [s]
+            while todo:
+                for t in self.eps[todo.pop()]:
+                    if not got >> t & 1:
+                        got |= 1 << t
+                        todo.append(t)
+            self._closure[s] = got
+        return got
+
+    def close(self, members: int) -> int:
+        out = 0
+        while members:
+            low = members & -members
+            out |= self.closure(low.bit_length() - 1)
+            members ^= low
+        return out
 
 
-def _parse_alternation(toks: Sequence[_Tok], begin: int) -> _Ast:
-    if len(toks) == 0:
-        raise RegexSyntaxError("Error: empty input at %d." % begin)
-    parts: List[_Ast] = []
-    depth = 0
-    last = 0
-    for i in range(len(toks) + 1):
-        if i == len(toks) or (_is(toks[i], "|") and depth == 0):
-            if last == 0 and i == len(toks):
-                return _parse_sequence(toks, begin)
-            parts.append(_parse_alternation(toks[last:i], begin + last))
-            last = i + 1
-        elif _is(toks[i], "("):
-            depth += 1
-        elif _is(toks[i], ")"):
-            depth -= 1
-    if len(parts) == 1:
-        return parts[0]
-    return _Ast("or", parts=parts)
-
-
-def _parse_sequence(toks: Sequence[_Tok], begin: int) -> _Ast:
-    if len(toks) == 0:
-        raise RegexSyntaxError("Error: empty input at %d." % begin)
-    parts: List[_Ast] = []
-    i = 0
-    n = len(toks)
-    while i < n:
-        t = toks[i]
-        if _is(t, "("):
-            last = i + 1
-            i += 1
-            depth = 1
-            while i < n and depth != 0:
-                if _is(toks[i], "("):
-                    depth += 1
-                elif _is(toks[i], ")"):
-                    depth -= 1
-                i += 1
-            if depth != 0:
-                raise RegexSyntaxError("Error: missing right bracket for %d." % (begin + last))
-            i -= 1
-            parts.append(_parse_alternation(toks[last:i], begin + last))
-        elif _is(t, "*"):
-            if not parts:
-                raise RegexSyntaxError("Error: unexpected * at %d." % (begin + i))
-            parts[-1] = _Ast("star", sub=parts[-1])
-        elif _is(t, "+"):
-            if not parts:
-                raise RegexSyntaxError("Error: unexpected + at %d." % (begin + i))
-            parts[-1] = _Ast("cat", parts=[parts[-1], _Ast("star", sub=parts[-1])])
-        elif _is(t, "?"):
-            if not parts:
-                raise RegexSyntaxError("Error: unexpected + at %d." % (begin + i))
-            parts[-1] = _Ast("or", parts=[parts[-1], _Ast("empty")])
-        elif _is(t, EPS):
-            parts.append(_Ast("empty"))
-        else:
-            parts.append(_Ast("text", text=t.ch))
-        i += 1
-    if len(parts) == 1:
-        return parts[0]
-    return _Ast("cat", parts=parts)
-
-
-def parse_regex(text: str) -> _Ast:
-    return _parse_alternation(_tokenise(text), 0)
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# syntax tree -> epsilon-NFA (regex.js:390-452).  State numbers are handed out in the order the reference's recursive
-# construction first enters / leaves a state; the subset keys, and through them every later order, depend on them.
-# ---------------------------------------------------------------------------------------------------------------------
-
-class _NfaState:
-    __slots__ = ("id", "accept", "edges")
-
-    def __init__(self, accept: bool = False):
-        self.id = -1
-        self.accept = accept
-        self.edges: List[Tuple[str, "_NfaState"]] = []
-
-
-def _thompson(node: _Ast, start: _NfaState, end: _NfaState, count: int) -> int:
-    if start.id < 0:
-        start.id = count
-        count += 1
-    k = node.kind
-    if k == "empty":
-        start.edges.append((EPS, end))
-    elif k == "text":
-        start.edges.append((node.text, end))
-    elif k == "cat":
-        last = start
-        for part in node.parts[:-1]:
-            mid = _NfaState()
-            count = _thompson(part, last, mid, count)
-            last = mid
-        count = _thompson(node.parts[-1], last, end, count)
-    elif k == "or":
-        for part in node.parts:
-            s, e = _NfaState(), _NfaState()
-            e.edges.append((EPS, end))
-            start.edges.append((EPS, s))
-            count = _thompson(part, s, e, count)
-    elif k == "star":
-        s, e = _NfaState(), _NfaState()
-        e.edges.append((EPS, s))
-        e.edges.append((EPS, end))
-        start.edges.append((EPS, s))
-        start.edges.append((EPS, end))
-        count = _thompson(node.sub, s, e, count)
-    else:  # pragma: no cover
-        raise AssertionError(k)
-    if end.id < 0:
-        end.id = count
-        count += 1
-    return count
-
-
-def regex_to_nfa(text: str) -> _NfaState:
-    ast = parse_regex(text)
-    start, accept = _NfaState(), _NfaState(accept=True)
-    limit = sys.getrecursionlimit()
-    sys.setrecursionlimit(max(limit, 100000))
-    try:
-        _thompson(ast, start, accept, 0)
-    finally:
-        sys.setrecursionlimit(limit)
-    return start
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# subset construction (regex.js:460-552)
-# ---------------------------------------------------------------------------------------------------------------------
-
-class _DfaState:
-    __slots__ = ("key", "items", "symbols", "accept", "trans", "id")
-
-    def __init__(self, key, items, symbols, accept):
-        self.key = key
-        self.items: List[_NfaState] = items
-        self.symbols: List[str] = symbols
-        self.accept: bool = accept
-        self.trans: Dict[str, "_DfaState"] = {}
-        self.id = ""
+def _bits(x: int):
+    while x:
+        low = x & -x
+        yield low.bit_length() - 1
+        x ^= low
 
 
 def _alpha_count(n: int) -> str:
-    """0 -> A, 25 -> Z, 26 -> AA ... (regex.js:517-527)."""
+    """0 -> A, 25 -> Z, 26 -> AA ...: the names the reference gives subset-construction states (regex.js:517-527)."""
     s = ""
     while n >= 0:
         s = chr(ord("A") + n % 26) + s
@@ -329,203 +306,83 @@ def _alpha_count(n: int) -> str:
     return s
 
 
-def _closure(seed: Sequence[_NfaState]) -> _DfaState:
-    seen: Dict[int, _NfaState] = {}
-    stack: List[_NfaState] = []
-    symbols: Set[str] = set()
-    accept = False
-    for s in seed:
-        stack.append(s)
-        seen[s.id] = s
-        accept |= s.accept
-    while stack:
-        top = stack.pop()
-        for sym, nxt in top.edges:
-            if sym == EPS:
-                if nxt.id not in seen:
-                    seen[nxt.id] = nxt
-                    stack.append(nxt)
-                    accept |= nxt.accept
-            else:
-                symbols.add(sym)
-    items = [seen[i] for i in sorted(seen)]
-    return _DfaState(",".join(str(s.id) for s in items), items, _js_sorted(symbols), accept)
+def _subset_dfa(text: str):
+    """Breadth-first subset construction, symbols in UTF-16 order.  Returns (transitions, accepting): state i has the edges
+    transitions[i] (symbol -> state), states are numbered in discovery order, 0 is the start."""
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))          # `add` recurses along the nesting depth of the pattern
+    nfa = _Nfa()
+    entry, final = nfa.new_state(), nfa.new_state()
+    nfa.add(parse_regex(text), entry, final)
+    index = {nfa.closure(entry): 0}
+    order = [nfa.closure(entry)]
+    transitions: List[Dict[str, int]] = []
+    moved: Dict[int, int] = {}                                          # closure of a target set, by the set
+    for members in order:                                              # grows while it is walked
+        out: Dict[str, int] = {}
+        for s in _bits(members):
+            for sym, targets in nfa.step[s].items():
+                out[sym] = out.get(sym, 0) | targets
+        edges: Dict[str, int] = {}
+        for sym in _js_sorted(out):
+            closed = moved.get(out[sym])
+            if closed is None:
+                closed = moved[out[sym]] = nfa.close(out[sym])
+            if closed not in index:
+                index[closed] = len(order)
+                order.append(closed)
+            edges[sym] = index[closed]
+        transitions.append(edges)
+    return transitions, [bool(m >> final & 1) for m in order]
 
 
-def _closed_move(state: _DfaState, symbol: str, memo: Dict[Tuple[int, ...], _DfaState]) -> _DfaState:
-    nexts: Dict[int, _NfaState] = {}
-    for item in state.items:
-        for sym, nxt in item.edges:
-            if sym == symbol:
-                nexts[nxt.id] = nxt
-    seed = tuple(sorted(nexts))             # a closure is a function of its seed set alone
-    hit = memo.get(seed)
-    if hit is None:
-        hit = memo[seed] = _closure(list(nexts.values()))
-    return hit
-
-
-def nfa_to_dfa(nfa: _NfaState) -> _DfaState:
-    first = _closure([nfa])
-    first.id = _alpha_count(0)
-    states = {first.key: first}
-    memo: Dict[Tuple[int, ...], _DfaState] = {}
-    queue = [first]
-    front = 0
-    while front < len(queue):
-        top = queue[front]
-        front += 1
-        for sym in top.symbols:
-            c = _closed_move(top, sym, memo)
-            known = states.get(c.key)
-            if known is None:
-                c.id = _alpha_count(len(states))
-                states[c.key] = c
-                queue.append(c)
-                known = c
-            top.trans[sym] = known
-    return first
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# Hopcroft minimisation and the merged-edge automaton (regex.js:560-762)
-# ---------------------------------------------------------------------------------------------------------------------
-
-class _MinState:
-    __slots__ = ("number", "accept", "trans")
-
-    def __init__(self, number: int, accept: bool):
-        self.number = number                # 1-based, the reference's "nature"
-        self.accept = accept
-        self.trans: Dict[str, "_MinState"] = {}     # merged label -> target
-
-
-def _reverse_edges(start: _DfaState):
-    symbols: Dict[str, bool] = {}
-    id_map: Dict[str, _DfaState] = {}
-    rev: Dict[str, Dict[str, List[str]]] = {}
-    visited = {start.id}
-    queue = [start]
-    front = 0
-    while front < len(queue):
-        top = queue[front]
-        front += 1
-        id_map[top.id] = top
-        for sym in top.symbols:
-            symbols.setdefault(sym, True)
-            nxt = top.trans[sym]
-            rev.setdefault(nxt.id, {}).setdefault(sym, []).append(top.id)
-            if nxt.id not in visited:
-                visited.add(nxt.id)
-                queue.append(nxt)
-    return _js_keys(symbols), id_map, rev
-
-
-def _hopcroft(symbols: List[str], id_map: Dict[str, _DfaState], rev) -> List[List[str]]:
-    ids = _js_sorted(id_map.keys())
-    partitions: Dict[str, List[str]] = {}
-    queue: List[Optional[str]] = []
-    visited: Dict[str, int] = {}
-    g1 = [i for i in ids if id_map[i].accept]
-    g2 = [i for i in ids if not id_map[i].accept]
-    key = ",".join(g1)
-    partitions[key] = g1
-    queue.append(key)
-    visited[key] = 0
-    if g2:
-        key = ",".join(g2)
-        partitions[key] = g2
-        queue.append(key)
-    front = 0
-    while front < len(queue):
-        top = queue[front]
-        front += 1
-        if not top:
-            continue
-        members = top.split(",")
-        for sym in symbols:
-            rev_group: Set[str] = set()
-            for m in members:
-                srcs = rev.get(m)
-                if srcs is not None and sym in srcs:
-                    rev_group.update(srcs[sym])
-            for key in _js_keys(partitions):
-                block = partitions[key]
-                g1 = [x for x in block if x in rev_group]
-                if not g1 or len(g1) == len(block):
-                    continue
-                g2 = [x for x in block if x not in rev_group]
-                del partitions[key]
-                k1, k2 = ",".join(g1), ",".join(g2)
-                partitions[k1] = g1
-                partitions[k2] = g2
-                if k1 in visited:
-                    queue[visited[k1]] = None
-                    visited[k1] = len(queue)
-                    queue.append(k1)
-                    visited[k2] = len(queue)
-                    queue.append(k2)
-                elif len(g1) <= len(g2):
-                    visited[k1] = len(queue)
-                    queue.append(k1)
-                else:
-                    visited[k2] = len(queue)
-                    queue.append(k2)
-    return [partitions[k] for k in _js_keys(partitions)]
-
-
-def _merge(start: _DfaState, partitions: List[List[str]], id_map, rev) -> List[_MinState]:
-    partitions.sort(key=lambda p: _utf16_key(",".join(p)))
-    for i, p in enumerate(partitions):
-        if start.id in p:
-            if i > 0:
-                partitions[i], partitions[0] = partitions[0], partitions[i]
+def _equivalence_classes(transitions, accepting) -> List[List[int]]:
+    """Coarsest partition of the (partial) DFA's states that separates accepting from other states and is stable under every
+    symbol; a missing edge is its own kind of target.  Refinement by signatures until nothing splits."""
+    cls = [1 if a else 0 for a in accepting]
+    count = len(set(cls))
+    while True:
+        seen: Dict[tuple, int] = {}
+        nxt = []
+        for i, edges in enumerate(transitions):
+            sig = (cls[i], tuple(sorted((sym, cls[t]) for sym, t in edges.items())))
+            nxt.append(seen.setdefault(sig, len(seen)))
+        cls = nxt
+        if len(seen) == count:
             break
-    group: Dict[str, int] = {}
-    nodes: List[_MinState] = []
-    for i, p in enumerate(partitions):
-        nodes.append(_MinState(i + 1, id_map[p[0]].accept))
-        for x in p:
-            group[x] = i
-    edges: List[Dict[int, Set[str]]] = [dict() for _ in partitions]
-    for to, by_sym in rev.items():
-        for sym, sources in by_sym.items():
-            for src in sources:
-                edges[group[src]].setdefault(group[to], set()).add(sym)
-    for frm, by_to in enumerate(edges):
-        for to in sorted(by_to):
-            nodes[frm].trans[_symbol_set_key(by_to[to])] = nodes[to]
-    return nodes
-
-
-def min_dfa(dfa: _DfaState) -> List[_MinState]:
-    symbols, id_map, rev = _reverse_edges(dfa)
-    return _merge(dfa, _hopcroft(symbols, id_map, rev), id_map, rev)
+        count = len(seen)
+    groups: Dict[int, List[int]] = {}
+    for i, c in enumerate(cls):
+        groups.setdefault(c, []).append(i)
+    return list(groups.values())
 
 
 def regex_to_dfa(regex: str) -> List[dict]:
     """`regexToDfa` (regex.js:40-90) as the parsed value of the JSON it returns: one `{"type", "edges"}` object per
     state, edges keyed by the JSON text of the sorted list of characters that share a target."""
-    nodes = min_dfa(nfa_to_dfa(regex_to_nfa(regex)))
-    reach: Dict[int, _MinState] = {}
-    stack = [nodes[0]]
-    labels: Set[str] = set()
-    while stack:
-        top = stack.pop()
-        if top.number in reach:
-            continue
-        reach[top.number] = top
-        for label, nxt in top.trans.items():
-            labels.add(label)
-            stack.append(nxt)
-    ordered = _js_sorted(labels)
-    size = max(reach)
-    graph: List[Optional[dict]] = [None] * size
-    for number in sorted(reach):
-        st = reach[number]
-        graph[number - 1] = {"type": "accept" if st.accept else "",
-                             "edges": {lab: st.trans[lab].number - 1 for lab in ordered if lab in st.trans}}
-    return graph
+    transitions, accepting = _subset_dfa(regex)
+    names = [_alpha_count(i) for i in range(len(transitions))]
+    classes = _equivalence_classes(transitions, accepting)
+    # the reference's numbering: classes ordered by the joined names of their members, then the start's class swapped to the front
+    keyed = []
+    for members in classes:
+        members = sorted(members, key=lambda i: _utf16_key(names[i]))
+        keyed.append((",".join(names[i] for i in members), members))
+    keyed.sort(key=lambda km: _utf16_key(km[0]))
+    at = next(k for k, (_, members) in enumerate(keyed) if 0 in members)
+    keyed[0], keyed[at] = keyed[at], keyed[0]
+    number = {}
+    for k, (_, members) in enumerate(keyed):
+        for i in members:
+            number[i] = k
+    # merged edges: every symbol that leads from class a to class b shares one label
+    merged: List[Dict[int, Set[str]]] = [dict() for _ in keyed]
+    for i, edges in enumerate(transitions):
+        for sym, t in edges.items():
+            merged[number[i]].setdefault(number[t], set()).add(sym)
+    labelled = [{_symbol_set_key(syms): to for to, syms in by_to.items()} for by_to in merged]
+    ordered = _js_sorted({lab for edges in labelled for lab in edges})
+    return [{"type": "accept" if accepting[members[0]] else "", "edges": {lab: labelled[k][lab] for lab in ordered if lab in labelled[k]}}
+            for k, (_, members) in enumerate(keyed)]
 
 
 def get_dfa_json_value(regex: str) -> List[dict]:

@@ -113,6 +113,23 @@ def test_parse_errors():
             vrm.regex_to_dfa(bad)
 
 
+def test_regex_to_dfa_known_answers():
+    """418 patterns whose DFA graphs were recorded from the round-1 port of regex.js (tools/make_vrm_golden.py) before the
+    regex -> DFA half of vrm.py was rewritten: the rewrite must give the same JSON text, state numbering and labels included."""
+    import hashlib
+    with open(Path(__file__).parent / "golden" / "vrm_dfa_cases.json") as f:
+        golden = json.load(f)
+    assert len(golden["cases"]) >= 400
+    for case in golden["cases"]:
+        text = vrm.dfa_json(vrm.regex_to_dfa(case["regex"]))
+        assert hashlib.sha256(text.encode("utf-8")).hexdigest() == case["sha256"], case["regex"]
+        if case["dfa_json"] is not None:
+            assert text == case["dfa_json"], case["regex"]
+    for bad in golden["syntax_errors"]:
+        with pytest.raises(vrm.RegexSyntaxError):
+            vrm.regex_to_dfa(bad)
+
+
 def test_back_graph_swap_remove_keeps_lists_consistent():
     g = vrm._BackGraph(3)
     e0 = g.add_edge(0, 1, "a")
