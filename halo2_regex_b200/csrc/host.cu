@@ -265,8 +265,13 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
     const uint64_t total = n ? h_offsets[n] : 0;
     const uint64_t base = n ? h_offsets[0] : 0;
     // every offset is checked before anything is enqueued: the kernels read bytes[offsets[j] .. offsets[j+1]) of the staging buffer
-    for (uint64_t j = 0; j < n; j++)
-        if (h_offsets[j + 1] < h_offsets[j]) { set_error("offsets must be non-decreasing (string %llu)", (unsigned long long)j); return B2R_ERR_INVALID_ARG; }
+    {
+        uint64_t bad = 0;                                                 // branch-free first pass (vectorisable), the index only if something is wrong
+        for (uint64_t j = 0; j < n; j++) bad |= (uint64_t)(h_offsets[j + 1] < h_offsets[j]);
+        if (bad)
+            for (uint64_t j = 0; j < n; j++)
+                if (h_offsets[j + 1] < h_offsets[j]) { set_error("offsets must be non-decreasing (string %llu)", (unsigned long long)j); return B2R_ERR_INVALID_ARG; }
+    }
     const uint64_t nbytes = total - base;
     const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
     if (!hook && c->opt.small_path && n >= 1 && n <= 32 && n * (rp * (4 + 3 * c->n_defs) + 2 * bp * c->n_defs) + nbytes <= (8u << 20))
@@ -352,7 +357,7 @@ int host_batch(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets,
     if (c->opt.slices >= 1 && c->opt.slices <= b2r_config::MAX_SLICES && n >= 16384) n_slices = c->opt.slices;   // testing hook
     // slice boundaries are multiples of 32 strings: whole tiles per slice, and lo * pitch keeps the 16-byte alignment of every
     // column for any legal pitch (bitmap_pitch is only a multiple of 4)
-    auto cut = [&](int k) { return k >= n_slices ? n : (n * (uint64_t)k / n_slices) & ~uint64_t(31); };
+    auto cut = [&](int k) { return k >= n_slices ? n : (n * (uint64_t)k / n_slices) & ~uint64_t(31); };   // (small first slices were tried: no gain)
 
     // ---- sparse mode: compaction arenas (device + pinned mirror) and the host threads ---------------------------------------------
     std::vector<const Copy*> scols;
