@@ -96,6 +96,11 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     const uint32_t P16 = TABLE_PLAIN16, P32 = TABLE_PLAIN;
     const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P16, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P16, HIST_GLOBAL},
                                  {P32, HIST_SMEM}, {P32, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
+    // a handful of tiles (the reference's one-string call): one CTA walks them, and staging 100 KB of replicated tables for it costs
+    // more than the bank conflicts of a few warps — a single copy of the tables
+    if (p.n_tiles <= 8 && force_table_mode < 0 && force_hist_mode < 0 && !p.segment_mode)
+        for (const uint32_t tm : {P32, P16})
+            if (fits(tm, HIST_SMEM, 4)) return B2R_OK;
     for (const auto& o : order) {
         if (force_table_mode >= 0 && (uint32_t)force_table_mode != o[0]) continue;   // testing hooks: honoured when they fit
         if (force_hist_mode >= 0 && (uint32_t)force_hist_mode != o[1]) continue;

@@ -164,31 +164,53 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     if (SMEM_TAB) {
         constexpr uint32_t csh = TM == (int)TABLE_REPL ? 5u : 0u;   // log2(copies)
 #pragma unroll
+        // (four global loads per thread in flight, then their stores: the shared-memory stores are compiler barriers, and a loop of
+        //  load -> store round trips made the prologue of a one-string launch 100 us long)
+        constexpr int SU = 4;
         for (int d = 0; d < D; d++) {
             const uint32_t n = p.def[d].num_classes * p.def[d].padded_states;
             const uint32_t t0 = base_s + lay.tab[d];
-            for (uint32_t i = threadIdx.x; i < (n << csh); i += blockDim.x) {
-                const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u);
-                const uint32_t e = __ldg(p.def[d].hot + idx);
-                // single-copy tables: row k is XOR-swizzled by its class (walk_swizzle) — lanes in the same state with
-                // different classes would otherwise all hit one bank (the row size is a power of two)
-                const uint32_t swz = TM == (int)TABLE_REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
-                if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
-                else sts32(t0 + ((idx * stride) ^ swz) + l * 4, e | ((e >> 16) * stride));
+            for (uint32_t i0 = threadIdx.x; i0 < (n << csh); i0 += SU * blockDim.x) {
+                uint32_t ev[SU];
+#pragma unroll
+                for (int u = 0; u < SU; u++) { const uint32_t i = i0 + u * blockDim.x; ev[u] = i < (n << csh) ? __ldg(p.def[d].hot + (i >> csh)) : 0u; }
+#pragma unroll
+                for (int u = 0; u < SU; u++) {
+                    const uint32_t i = i0 + u * blockDim.x;
+                    if (i >= (n << csh)) break;
+                    const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u), e = ev[u];
+                    // single-copy tables: row k is XOR-swizzled by its class (walk_swizzle) — lanes in the same state with
+                    // different classes would otherwise all hit one bank (the row size is a power of two)
+                    const uint32_t swz = TM == (int)TABLE_REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
+                    if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
+                    else sts32(t0 + ((idx * stride) ^ swz) + l * 4, e | ((e >> 16) * stride));
+                }
             }
         }
-        for (uint32_t i = threadIdx.x; i < (256u << csh); i += blockDim.x) {
-            const uint32_t c = i >> csh, l = i & ((1u << csh) - 1u);
-            uint32_t v;
-            if (D == 1) {
-                const uint32_t k = __ldg(p.def[0].byte_class + c), rb = p.def[0].padded_states * stride;
-                v = base_s + lay.tab[0] + k * rb + l * 4 + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rb));
-            } else {
-                v = 0;
+        for (uint32_t i0 = threadIdx.x; i0 < (256u << csh); i0 += SU * blockDim.x) {
+            uint32_t kv4[SU][D];
 #pragma unroll
-                for (int d = 0; d < D; d++) v |= (uint32_t)__ldg(p.def[d].byte_class + c) << (8 * d);
+            for (int u = 0; u < SU; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+#pragma unroll
+                for (int d = 0; d < D; d++) kv4[u][d] = i < (256u << csh) ? (uint32_t)__ldg(p.def[d].byte_class + (i >> csh)) : 0u;
             }
-            sts32(base_s + lay.cls + c * cstride + l * 4, v);
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i >= (256u << csh)) break;
+                const uint32_t c = i >> csh, l = i & ((1u << csh) - 1u);
+                uint32_t v;
+                if (D == 1) {
+                    const uint32_t k = kv4[u][0], rb = p.def[0].padded_states * stride;
+                    v = base_s + lay.tab[0] + k * rb + l * 4 + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rb));
+                } else {
+                    v = 0;
+#pragma unroll
+                    for (int d = 0; d < D; d++) v |= kv4[u][d] << (8 * d);
+                }
+                sts32(base_s + lay.cls + c * cstride + l * 4, v);
+            }
         }
     }
     if (HM == (int)HIST_SMEM) {
@@ -408,6 +430,8 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             for (int g = 0; g < DCH / 16; g++) {
                 const uint32_t gbase = cbase + g * 16;
                 if (gbase >= Mpad) break;
+                if (!valid) continue;                                   // a lane without a string (partial tile): its rows are never stored; without this it would drag
+                                                                        // the warp through the byte-by-byte ragged path in every granule (a one-string call: 196 us -> see DESIGN)
                 uint32_t w[4];
                 if (!any_shift) {
                     const uint4 v = lds128(my_in + g * 16);
