@@ -175,6 +175,10 @@ bool is_pinned(const void* h) {
 // the first three parts go up in one copy, everything from the multiplicity block on comes back in one copy.
 int host_batch_small(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_offsets, uint64_t n, const b2r_outputs* ho, b2r_batch_status* result) {
     cudaStream_t st = c->host_stream;
+    const bool trace = c->opt.trace_host;
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto wall_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - wall0).count(); };
+    double w_prep = 0, w_up = 0, w_enq = 0, w_sync = 0;
     const uint64_t base = h_offsets[0], nbytes = h_offsets[n] - base;
     const uint64_t rp = ho->row_pitch, bp = ho->bitmap_pitch;
     const bool acc = (ho->flags & B2R_OUT_ACCUMULATE_MULT) != 0;
@@ -227,15 +231,22 @@ int host_batch_small(b2r_config* c, const uint8_t* h_bytes, const uint64_t* h_of
         for (const Part& p : parts) if (p.off < mult_end) memcpy(hv + p.off, p.host, p.bytes);
         up_bytes = mult_end;
     }
+    w_prep = wall_us();
     CUDA_TRY(cudaMemcpyAsync(dv, hv, up_bytes, cudaMemcpyHostToDevice, st));
+    w_up = wall_us();
     dout.flags &= ~(uint32_t)B2R_OUT_SPARSE_D2H;                          // nothing to gain on one tile
     c->counters_copy = (BatchCounters*)(dv + off_cnt);
     rc = match_batch_impl(c, dv + off_bytes, (const uint64_t*)(dv + off_offs), n, shift + nbytes, &dout, c->max_chars, st);
     c->counters_copy = nullptr;
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(hv + off_mult, dv + off_mult, need - off_mult, cudaMemcpyDeviceToHost, st));
+    w_enq = wall_us();
     CUDA_TRY(cudaStreamSynchronize(st));
+    w_sync = wall_us();
     for (const Part& p : parts) memcpy(p.host, hv + p.off, p.bytes);
+    if (trace)
+        fprintf(stderr, "[b2r] small batch (%llu strings): staged %.1f us, H2D issued %.1f, kernels + D2H issued %.1f, device done %.1f, copied out %.1f\n", (unsigned long long)n, w_prep,
+                w_up, w_enq, w_sync, wall_us());
     c->last_h2d_bytes = up_bytes; c->last_d2h_bytes = need - off_mult;
     const BatchCounters* hc = (const BatchCounters*)(hv + off_cnt);
     b2r_batch_status r;

@@ -16,3 +16,6 @@ for _ in range(200):
     t = time.perf_counter(); r = cfg.match_substrs(s); ts.append(time.perf_counter() - t)
 ts.sort()
 print(f"match_substrs 1 KiB: p50 {ts[100] * 1e6:.1f} us, p10 {ts[20] * 1e6:.1f}, p99 {ts[198] * 1e6:.1f}; launches {cfg.last_launch_count()}")
+cfg.set_option("trace_host", 1)
+for _ in range(3):
+    cfg.match_substrs(s)
