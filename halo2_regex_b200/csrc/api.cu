@@ -79,7 +79,7 @@ void read_env_options(b2r_config* c) {
     if (const char* e = getenv("B2R_HIST_MODE")) o.force_hist_mode = parse_hist_mode(e);
     if (const char* e = getenv("B2R_DEBUG")) o.debug = (uint32_t)atoi(e);
     if (const char* e = getenv("B2R_SPREAD_FILL")) o.spread_fill = e[0] == '0' ? 0u : 1u;
-    if (const char* e = getenv("B2R_FUSE")) o.fuse = e[0] == '0' ? 0u : 1u;
+    if (const char* e = getenv("B2R_FUSE")) o.fuse = atoi(e);
     if (const char* e = getenv("B2R_STAGGER_NS")) o.stagger_ns = atoi(e);
     if (const char* e = getenv("B2R_SLICES")) o.slices = atoi(e);
     o.trace_host = getenv("B2R_TRACE_HOST") != nullptr;
@@ -128,7 +128,10 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
-    p.debug = c->opt.debug; p.spread_fill = c->opt.spread_fill; p.fuse = c->opt.fuse;
+    p.debug = c->opt.debug; p.spread_fill = c->opt.spread_fill; {
+        const int mode = c->opt.fuse >= 0 && c->opt.fuse <= 2 ? c->opt.fuse : (c->n_defs <= 2 ? 1 : 2);
+        p.fuse = mode == 1 ? 1u : 0u; p.fill_in_walk = mode == 2 ? 1u : 0u;
+    }
     // offset warp starts (walk.cuh) pay off for one def on batches of many tiles per warp: config 1 1.444 -> 1.408 ms, config 2 reading (i)
     // 54.3 -> 56.8 %, the 1023-state DFA 36.5 -> 37 %; three defs lose (35.0 -> 34.2 %), so they keep starting together
     p.stagger_ns = c->opt.stagger_ns >= 0 ? (uint32_t)c->opt.stagger_ns : (c->n_defs == 1 && p.n_tiles >= 4u * 148u * 16u ? 3u * (uint32_t)max_chars : 0u);
@@ -196,7 +199,9 @@ int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_of
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], st));
     if (n && !p.fuse) {
-        if ((rc = launch_emit(p, wide, st, nullptr))) return rc;
+        WalkParams pe = p;
+        pe.prefilled = p.fill_in_walk;                                    // the walk has zeroed the sparse columns of every tile
+        if ((rc = launch_emit(pe, wide, st, nullptr))) return rc;
         c->last_launches++;
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], st));
@@ -522,7 +527,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     seg.row_pitch = LONG_CHUNK;
     WalkParams pw;
     fill_walk_params(c, pw, d_bytes, d_offsets, n_chunks, len, &seg, LONG_CHUNK + 1);
-    pw.fuse = 0; pw.prefilled = 0; pw.segment_mode = 1; pw.stagger_ns = 0;
+    pw.fuse = 0; pw.fill_in_walk = 0; pw.prefilled = 0; pw.segment_mode = 1; pw.stagger_ns = 0;
     pw.summary = (uint32_t*)(ws + off_summary); pw.summary2 = (uint32_t*)(ws + off_summary2);   // written by the walk itself (two flag words per chunk)
     pw.fmask = (uint32_t*)(ws + off_fmask);
     for (uint32_t d = 0; d < c->n_defs; d++) {
@@ -539,7 +544,7 @@ int b2r_match_long(b2r_config* c, const uint8_t* d_bytes, uint64_t len, const b2
     CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[0], 0));
     WalkParams& pe = c->last;
     fill_walk_params(c, pe, d_bytes, d_offsets + n_chunks + 1, 1, len, o, M);
-    pe.fuse = 0; pe.prefilled = 1;
+    pe.fuse = 0; pe.fill_in_walk = 0; pe.prefilled = 1;
     pe.fmask = pw.fmask;
     for (uint32_t d = 0; d < c->n_defs; d++) pe.def[d].states = pw.def[d].states;
     c->have_last = true;
@@ -562,7 +567,7 @@ int b2r_config_set_option(b2r_config* c, const char* name, const char* value) {
     else if (!strcmp(name, "hist_mode")) o.force_hist_mode = parse_hist_mode(value);
     else if (!strcmp(name, "debug")) o.debug = (uint32_t)v;
     else if (!strcmp(name, "spread_fill")) o.spread_fill = v ? 1u : 0u;
-    else if (!strcmp(name, "fuse")) o.fuse = v ? 1u : 0u;
+    else if (!strcmp(name, "fuse")) o.fuse = v < 0 || v > 2 ? -1 : v;
     else if (!strcmp(name, "stagger_ns")) o.stagger_ns = v;
     else if (!strcmp(name, "slices")) o.slices = v;
     else if (!strcmp(name, "trace_host")) o.trace_host = v != 0;

@@ -132,7 +132,8 @@ struct b2r_config {
         uint32_t debug = 0;           // timing experiments only: emit skips 1 zero-fill, 2 scan, 4 final-state loads, 8 status
         uint32_t spread_fill = 1;
         int stagger_ns = -1;          // start offset between the warps of a walk CTA (-1 = default, see plan in api.cu)
-        uint32_t fuse = 1;            // 0: emit_kernel as its own launch
+        int fuse = -1;                // 1: walk_kernel runs the emit stage itself; 0: emit_kernel as its own launch (it also zero-fills); 2: emit_kernel as its
+                                      // own launch, but the walk zero-fills; -1: 1 for one or two defs, 2 for more
         int slices = 0;               // host entry point: slices per batch (0 = default)
         bool trace_host = false;
         int hist_cache_log2 = 0;      // 0 = default

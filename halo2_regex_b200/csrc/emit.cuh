@@ -535,7 +535,7 @@ struct TileEmitter {
     }
 
     // stand-alone entry: everything about the tile's strings comes from global memory
-    __device__ __forceinline__ void run_tile_from_memory(uint64_t tile, EmitTotals& tot) {
+    __device__ __forceinline__ void run_tile_from_memory(uint64_t tile, EmitTotals& tot, bool filled) {
         const uint64_t N = p.n_strings;
         const uint32_t M = p.max_chars;
         const uint64_t tile_base = tile * 32;
@@ -553,7 +553,7 @@ struct TileEmitter {
 #pragma unroll
         for (int d = 0; d < D; d++)
             fin[d] = (live && !(p.debug & 4)) ? (uint32_t)__ldcg(reinterpret_cast<const ST*>(p.def[d].states) + jl * p.row_pitch + Ll) : 0xFFFFFFFEu;
-        run_tile(tile_base, valid, live, live ? off : 0ull, Ll, fw0, fw1, fin, tot, /*filled=*/p.prefilled != 0);
+        run_tile(tile_base, valid, live, live ? off : 0ull, Ll, fw0, fw1, fin, tot, filled);
     }
 };
 
@@ -615,23 +615,74 @@ __device__ __forceinline__ void emit_publish(const WalkParams& p, const EmitTabl
     }
 }
 
+// Zero-fill of one tile's rows of every sparse column with TMA bulk stores (shared zero buffer -> global), lane-strided; the
+// caller commits the bulk group.  The rows of a tile are contiguous in every column.  zero_s: EMIT_ZERO_BYTES of zeros.
+constexpr uint32_t EMIT_ZERO_BYTES = 4096;
+template <int D>
+__device__ __forceinline__ void emit_issue_tile_fill(const WalkParams& p, uint64_t tile, int lane, uint32_t zero_s) {
+    const uint64_t tile_base = tile * 32;
+    const uint64_t rows_here = p.n_strings - tile_base < 32 ? p.n_strings - tile_base : 32;
+    const uint64_t cbytes = rows_here * p.row_pitch, bbytes = rows_here * p.bitmap_pitch;
+    uint32_t first = 0;
+    auto region = [&](uint8_t* ptr, uint64_t bytes) {
+        if (!ptr) return;
+        const uint32_t bulk_bytes = (uint32_t)(bytes & ~15ull);            // bitmap regions of a partial tile can end on a 4-byte boundary
+        const uint32_t n_ops = (bulk_bytes + EMIT_ZERO_BYTES - 1) / EMIT_ZERO_BYTES;
+        for (uint32_t op = ((uint32_t)lane + 32u - (first & 31u)) & 31u; op < n_ops; op += 32) {
+            const uint32_t o = op * EMIT_ZERO_BYTES;
+            const uint32_t nb = bulk_bytes - o < EMIT_ZERO_BYTES ? bulk_bytes - o : EMIT_ZERO_BYTES;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ptr + o), "r"(zero_s), "r"(nb) : "memory");
+        }
+        for (uint64_t o = bulk_bytes + (uint64_t)lane * 4; o < bytes; o += 128) *reinterpret_cast<uint32_t*>(ptr + o) = 0u;
+        first += n_ops;
+    };
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        region(p.def[d].substr_ids ? p.def[d].substr_ids + tile_base * p.row_pitch : nullptr, cbytes);
+        region(p.def[d].start_enable ? p.def[d].start_enable + tile_base * p.bitmap_pitch : nullptr, bbytes);
+        region(p.def[d].end_enable ? p.def[d].end_enable + tile_base * p.bitmap_pitch : nullptr, bbytes);
+    }
+    region(p.masked_chars ? p.masked_chars + tile_base * p.row_pitch : nullptr, cbytes);
+    region(p.masked_substr_ids ? p.masked_substr_ids + tile_base * p.row_pitch : nullptr, cbytes);
+}
+
+// The emit stage as its own kernel (the walk ran first; B2R_FUSE=0, and the default for three or more defs: there the fused kernel's
+// code no longer fits the instruction caches — 34 % of its warp samples were instruction-fetch stalls — and walk + emit as two
+// kernels take 4.0 instead of 4.7 ms per 2^20 strings).  Tiles are handed out by an atomic counter.  The zero-fill of the NEXT tile
+// (TMA bulk stores, asynchronous) is in flight while the current tile is scanned: fill and scan overlap instead of adding up.
 template <int D, typename ST>
 __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char esmem[];
+    __shared__ __align__(128) unsigned char zero_buf[EMIT_ZERO_BYTES];
     const int lane = threadIdx.x & 31;
     EmitTables<D> tb;
     emit_tables_init<D>(p, esmem, tb);
+    const bool fill = !p.prefilled && !(p.debug & 1);
+    for (uint32_t i = threadIdx.x * 16; i < EMIT_ZERO_BYTES; i += blockDim.x * 16) *reinterpret_cast<uint4*>(zero_buf + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // zero buffer -> visible to the TMA (async proxy)
     __syncthreads();
+    const uint32_t zero_s = (uint32_t)__cvta_generic_to_shared(zero_buf);
 
     TileEmitter<D, ST> em(p, tb, lane);
     EmitTotals tot;
-    for (;;) {   // tiles handed out by an atomic counter: the work per tile varies with the strings
+    auto fetch = [&]() -> unsigned long long {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(&p.counters->emit_tile_counter, 1ull);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= p.n_tiles) break;
-        em.run_tile_from_memory(t, tot);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    unsigned long long t = fetch();
+    if (fill && t < p.n_tiles) emit_issue_tile_fill<D>(p, t, lane, zero_s);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    while (t < p.n_tiles) {
+        const unsigned long long t_next = fetch();
+        if (fill && t_next < p.n_tiles) emit_issue_tile_fill<D>(p, t_next, lane, zero_s);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");      // the zeros of tile t are in place (mine ...
+        __syncwarp();                                                    // ... and those of the other lanes)
+        em.run_tile_from_memory(t, tot, /*filled=*/true);
+        t = t_next;
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     emit_publish<D>(p, tb, tot);
 }
 

@@ -165,7 +165,7 @@ int launch_emit(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen
     const size_t smem = emit_smem_bytes(p);
     const int wpc = EMIT_THREADS / 32;
     int per_sm = 2048 / EMIT_THREADS;
-    if (smem) { const int by_smem = (int)((size_t)max_smem / (smem + 1024)); if (by_smem < per_sm) per_sm = by_smem < 1 ? 1 : by_smem; }
+    { const int by_smem = (int)((size_t)max_smem / (smem + EMIT_ZERO_BYTES + 1024)); if (by_smem < per_sm) per_sm = by_smem < 1 ? 1 : by_smem; }   // + the static zero buffer
     const long long want = ((long long)p.n_tiles + wpc - 1) / wpc;   // one warp per tile of 32 strings
     long long grid = (long long)n_sm * per_sm;
     if (grid > want) grid = want > 0 ? want : 1;

@@ -79,6 +79,8 @@ struct WalkParams {
     uint32_t* summary;               // segment mode: one bit per chunk "has a flagged granule" (one word per tile), and
     uint32_t* summary2;              //   one bit per summary word (zeroed by the caller); null: not wanted
     uint32_t fuse;                   // 1: walk_kernel runs the emit stage itself, tile by tile (no emit_kernel launch)
+    uint32_t fill_in_walk;           // fuse == 0: walk_kernel still zero-fills the sparse columns of its tiles (TMA stores spread over the chunk loop,
+                                     //   as in fused mode); emit_kernel then runs with prefilled = 1 and only scans
     uint32_t prefilled;              // 1: the sparse columns were zeroed before the emit stage runs (long-string path: memset)
     uint32_t spread_fill;            // 1: the fused zero-fill ops are issued across the chunk loop instead of in one burst per tile
     uint32_t stagger_ns;             // warp w of a CTA starts w * stagger_ns late: the warps' walk and emit phases interleave instead of coinciding

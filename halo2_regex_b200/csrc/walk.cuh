@@ -116,7 +116,7 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
     if (p.fuse) cur += emit_smem_bytes(p);
     cur = walk_align_up(cur, 128);
     L.zero = cur;
-    if (p.fuse) cur += WALK_ZERO_BYTES;
+    if (p.fuse || p.fill_in_walk) cur += WALK_ZERO_BYTES;
     L.tiles = cur;
     // per warp: two input tiles (double buffer); a state tile per def — except for one def with 1-byte states, whose states
     // overwrite the consumed bytes of the current input tile; the stash of one flagged granule per lane (fused emit stage)
@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     }
     EmitTables<D> etb;
     const uint32_t zero_s = base_s + lay.zero;
-    if (p.fuse) {
-        emit_tables_init<D>(p, dsmem + (base_s - smem_u32(dsmem)) + lay.emit, etb);
+    const bool fillw = p.fuse || p.fill_in_walk;                        // this kernel zero-fills the sparse columns of its tiles
+    if (p.fuse) emit_tables_init<D>(p, dsmem + (base_s - smem_u32(dsmem)) + lay.emit, etb);
+    if (fillw) {
         for (uint32_t i = threadIdx.x * 16; i < WALK_ZERO_BYTES; i += blockDim.x * 16) sts128(zero_s + i, 0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zero buffer -> visible to the TMA (async proxy)
     }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         // (the issuing warps stall) and bunches the HBM writes in front of the other warps' input loads.
         uint8_t *dz_ptr0 = nullptr, *dz_ptr1 = nullptr;
         uint32_t dz_bytes0 = 0u, dz_bytes1 = 0u, dz_chunk0 = NO_POS, dz_chunk1 = NO_POS;
-        if (p.fuse && !(p.debug & 1)) {
+        if (fillw && !(p.debug & 1)) {
             const uint64_t cbytes = (uint64_t)rows_here * rp, bbytes = (uint64_t)rows_here * p.bitmap_pitch;
             uint8_t* reg_ptr[3 * D + 2];
             uint64_t reg_bytes[3 * D + 2];
@@ -589,10 +590,12 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             }
         }
         // ---- fused emit stage: the tile's states are in L1/L2, its flags and final states in registers --------------------
-        if (p.fuse) {
+        if (fillw) {
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my zero-fill stores have completed ...
             __syncwarp();                                                 // ... and so have those of the other lanes
+        }
+        if (p.fuse) {
 #ifdef B2R_PROBE
             const unsigned long long pr_t3 = gtime();
 #endif

@@ -223,7 +223,7 @@ def test_device_pointer_entry_point():
         out = H.DeviceOutputs(cfg, len(strings), max_records=8, compact_pitch=64)
         cfg.match_batch_device(d_bytes, d_offs, out, stream=stream)
         res = cfg.batch_result(stream=stream)
-    assert res.code == 0 and cfg.last_launch_count() == 2      # walk (emit stage fused in), finalize
+    assert res.code == 0 and cfg.last_launch_count() == 3      # three defs: walk (+ zero-fill), emit, finalize
     o, _ = ocfg.match_batch(data, offs, max_records=8, compact_pitch=64)
     assert H.compare_outputs(out.to_host(), o) == []
 
@@ -242,14 +242,23 @@ def test_table_and_bin_placements(monkeypatch, set_name, table_mode, hist_mode):
         assert cfg.last_plan()[0] == table_mode
 
 
-@pytest.mark.parametrize("set_name", ["regex1", "test1", "regex3_k3"])
-def test_separate_emit_kernel(monkeypatch, set_name):
-    """B2R_FUSE=0: the emit stage as its own kernel after the walk (the default runs it inside walk_kernel, tile by tile)."""
-    monkeypatch.setenv("B2R_FUSE", "0")
+@pytest.mark.parametrize("set_name,fuse", [("regex1", 0), ("test1", 0), ("regex3_k3", 0), ("three", 0), ("three", 1), ("regex1", 1), ("three", 2), ("regex1", 2), ("test1", 2)])
+def test_emit_stage_fused_and_separate(monkeypatch, set_name, fuse):
+    """B2R_FUSE=1: the emit stage inside walk_kernel, tile by tile (the default for one or two defs); 2: the walk zero-fills, the emit
+    stage scans as its own kernel (the default for three or more); 0: the emit kernel does both."""
+    monkeypatch.setenv("B2R_FUSE", str(fuse))
     rng = random.Random(zlib.crc32(set_name.encode()) + 7)
     strings = _random_strings(rng, 500, 300, SNIPPETS) + [b"", b"zz"]
     cfg, g, o = _both(set_name, 301, strings)
-    assert cfg.last_launch_count() == 3
+    assert cfg.last_launch_count() == (2 if fuse == 1 else 3)
+
+
+def test_default_emit_placement():
+    rng = random.Random(11)
+    strings = _random_strings(rng, 200, 120, SNIPPETS)
+    for set_name, launches in (("regex1", 2), ("test1", 2), ("three", 3)):
+        cfg, g, o = _both(set_name, 121, strings)
+        assert cfg.last_launch_count() == launches, set_name
 
 
 def test_wide_state_column():
