@@ -129,7 +129,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
     p.counters = (BatchCounters*)c->scratch;
     p.n_tiles = (uint32_t)((n + 31) / 32);
     p.debug = c->opt.debug; p.spread_fill = c->opt.spread_fill; {
-        const int mode = c->opt.fuse >= 0 && c->opt.fuse <= 2 ? c->opt.fuse : (c->n_defs <= 2 ? 1 : 2);
+        const int mode = c->opt.fuse >= 0 && c->opt.fuse <= 2 ? c->opt.fuse : (c->n_defs <= 1 ? 1 : 2);
         p.fuse = mode == 1 ? 1u : 0u; p.fill_in_walk = mode == 2 ? 1u : 0u;
     }
     // offset warp starts (walk.cuh) pay off for one def on batches of many tiles per warp: config 1 1.444 -> 1.408 ms, config 2 reading (i)
@@ -191,6 +191,12 @@ int match_batch_impl(b2r_config* c, const uint8_t* d_bytes, const uint64_t* d_of
             p.def[d].states = c->ws_states[d].p;
         }
         if ((rc = plan_walk(p, wide, c->opt.force_table_mode, c->opt.force_hist_mode, c->opt.hist_cache_log2))) return rc;
+        // one def stays fused only with replicated tables (a small DFA): the large-DFA kernel is better off with the emit stage as
+        // its own launch as well (1023 states: 5.57 -> 5.34 ms)
+        if (c->opt.fuse < 0 && p.fuse && p.table_mode != TABLE_REPL && p.n_tiles > 8) {
+            p.fuse = 0; p.fill_in_walk = 1;
+            if ((rc = plan_walk(p, wide, c->opt.force_table_mode, c->opt.force_hist_mode, c->opt.hist_cache_log2))) return rc;
+        }
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], st));
     if (n) {

@@ -133,7 +133,7 @@ struct b2r_config {
         uint32_t spread_fill = 1;
         int stagger_ns = -1;          // start offset between the warps of a walk CTA (-1 = default, see plan in api.cu)
         int fuse = -1;                // 1: walk_kernel runs the emit stage itself; 0: emit_kernel as its own launch (it also zero-fills); 2: emit_kernel as its
-                                      // own launch, but the walk zero-fills; -1: 1 for one or two defs, 2 for more
+                                      // own launch, but the walk zero-fills; -1: 1 for one def with replicated tables, else 2
         int slices = 0;               // host entry point: slices per batch (0 = default)
         bool trace_host = false;
         int hist_cache_log2 = 0;      // 0 = default

@@ -256,7 +256,7 @@ def test_emit_stage_fused_and_separate(monkeypatch, set_name, fuse):
 def test_default_emit_placement():
     rng = random.Random(11)
     strings = _random_strings(rng, 200, 120, SNIPPETS)
-    for set_name, launches in (("regex1", 2), ("test1", 2), ("three", 3)):
+    for set_name, launches in (("regex1", 2), ("test1", 3), ("three", 3)):
         cfg, g, o = _both(set_name, 121, strings)
         assert cfg.last_launch_count() == launches, set_name
 
