@@ -68,7 +68,7 @@ int upload_tables(b2r_config* c) {
 }
 
 int parse_table_mode(const char* tm) {
-    return !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "plain16") ? (int)TABLE_PLAIN16 : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
+    return !strcmp(tm, "repl") ? (int)TABLE_REPL : !strcmp(tm, "repl16") ? (int)TABLE_REPL16 : !strcmp(tm, "plain") ? (int)TABLE_PLAIN : !strcmp(tm, "plain16") ? (int)TABLE_PLAIN16 : !strcmp(tm, "global") ? (int)TABLE_GLOBAL : -1;
 }
 int parse_hist_mode(const char* hm) { return !strcmp(hm, "smem") ? (int)HIST_SMEM : !strcmp(hm, "global") ? (int)HIST_GLOBAL : -1; }
 

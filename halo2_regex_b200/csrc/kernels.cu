@@ -94,8 +94,9 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     // (single copy: the 16-bit entries win at every size measured — two entries per bank word halve the conflicts and
     //  the footprint: 3-def set 28.9 % -> 31.9 % of HBM peak, 2-def 40.1 -> 43.3, 1023-state DFA 2.2x)
     const uint32_t P16 = TABLE_PLAIN16, P32 = TABLE_PLAIN;
+    // (TABLE_REPL16 is only taken when asked for: see DESIGN, "three defs")
     const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P16, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P16, HIST_GLOBAL},
-                                 {P32, HIST_SMEM}, {P32, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}};
+                                 {P32, HIST_SMEM}, {P32, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}, {TABLE_REPL16, HIST_SMEM}, {TABLE_REPL16, HIST_GLOBAL}};
     // a handful of tiles (the reference's one-string call): one CTA walks them, and staging 100 KB of replicated tables for it costs
     // more than the bank conflicts of a few warps — a single copy of the tables
     if (p.n_tiles <= 8 && force_table_mode < 0 && force_hist_mode < 0 && !p.segment_mode)
@@ -109,6 +110,7 @@ int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mod
     for (const int need : {MIN_WARPS_REPL, 4})
         for (const auto& o : order) {
             if (o[0] == TABLE_GLOBAL && need != 4) continue;                       // global tables: the last resort
+            if (o[0] == TABLE_REPL16 && force_table_mode != (int)TABLE_REPL16) continue;
             if (fits(o[0], o[1], o[0] == TABLE_REPL ? MIN_WARPS_REPL : need)) return B2R_OK;
         }
     set_error("walk_kernel: no table placement fits in shared memory");

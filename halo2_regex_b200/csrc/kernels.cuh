@@ -69,7 +69,7 @@ struct WalkParams {
     // transition in some def.  Word w of string j lives at fmask[w * n_strings + j]; fm_words = ceil(ceil((M-1)/16) / 32).
     uint32_t* fmask;
     uint32_t fm_words;
-    uint32_t table_mode;             // TABLE_REPL / TABLE_PLAIN / TABLE_GLOBAL (walk.cuh)
+    uint32_t table_mode;             // TABLE_REPL / TABLE_REPL16 / TABLE_PLAIN / TABLE_PLAIN16 / TABLE_GLOBAL (walk.cuh)
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t hist_cache_log2;        // HIST_GLOBAL: log2 of the slots of the per-def shared-memory bin cache in front of L2
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)
@@ -91,6 +91,8 @@ constexpr uint32_t TABLE_REPL = 0;   // shared memory, one copy of every entry p
 constexpr uint32_t TABLE_PLAIN = 1;  // shared memory, one copy (stride 4 B)
 constexpr uint32_t TABLE_GLOBAL = 2; // global memory (L1/L2)
 constexpr uint32_t TABLE_PLAIN16 = 3; // shared memory, one copy of 16-bit entries (next << 1 | rare): half the size, for large DFAs
+constexpr uint32_t TABLE_REPL16 = 4;  // shared memory, 16-bit entries (next << 6 | rare) replicated once per lane (stride 64 B: two lanes share a bank word,
+                                      // no conflict): conflict-free lookups at half the footprint of TABLE_REPL — several small DFAs side by side
 // HIST_SMEM: dense bins [state][byte] in shared memory.  HIST_GLOBAL (bins too large for that): 64-bit atomics on the global
 // bins, behind a shared-memory cache of (key, count) slots that absorbs the hot (byte, state) pairs.
 constexpr uint32_t HIST_NONE = 0, HIST_SMEM = 1, HIST_GLOBAL = 2;

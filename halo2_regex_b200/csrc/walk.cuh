@@ -77,8 +77,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // bytes between consecutive table entries; class-table entries are 4 bytes (128 when replicated)
 // in-row XOR swizzle of class row k of a single-copy table (row_bytes = padded_states * stride, a power of two): words
 __host__ __device__ inline uint32_t walk_swizzle(uint32_t k, uint32_t row_bytes) { return (k << 2) & (row_bytes - 1u) & 0x7Cu; }
-__host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : table_mode == TABLE_PLAIN16 ? 2u : 4u; }
-__host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : 4u; }
+__host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : table_mode == TABLE_REPL16 ? 64u : table_mode == TABLE_PLAIN16 ? 2u : 4u; }
+__host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode) { return table_mode == TABLE_REPL || table_mode == TABLE_REPL16 ? 128u : 4u; }
 __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
 struct WalkLayout {
@@ -132,7 +132,7 @@ __host__ __device__ inline size_t walk_smem_bytes(const WalkParams& p, uint32_t 
     return (size_t)L.align + L.tiles + (size_t)warps * L.per_warp;   // + align: the dynamic base is only 16-byte aligned
 }
 
-// TM: TABLE_REPL, TABLE_PLAIN, TABLE_PLAIN16 or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
+// TM: TABLE_REPL, TABLE_REPL16, TABLE_PLAIN, TABLE_PLAIN16 or TABLE_GLOBAL.  HM: HIST_SMEM or HIST_GLOBAL.
 template <int D, typename ST, int TM, int HM>
 __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_constant__ WalkParams p) {
     constexpr int DCH = WALK_DCH, PITCH = WALK_PITCH;
@@ -154,15 +154,19 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     // bytes per zero-fill op: smaller ops spread more evenly over the chunk loop (one def: 58 ops of 2 KB, two per lane;
     // 1.45 -> 1.43 ms on config 1; 8 KB ops: 1.50 ms), but a lane defers at most two, so more defs keep 4 KB ops
     constexpr uint32_t ZOP = D == 1 ? 2048u : WALK_ZERO_BYTES;
-    constexpr bool E16 = TM == (int)TABLE_PLAIN16;                       // 16-bit entries: next << 1 | rare (else next << 16 | next * stride | rare)
-    constexpr uint32_t NSH = E16 ? 1u : 16u;                            // entry >> NSH = the state
-    constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
-    constexpr uint32_t cstride = TM == (int)TABLE_REPL ? 128u : 4u;       // class-table entry stride
-    const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : 0u;
+    constexpr bool REPL = TM == (int)TABLE_REPL || TM == (int)TABLE_REPL16;   // one copy of every entry per lane
+    constexpr bool E16 = TM == (int)TABLE_PLAIN16 || TM == (int)TABLE_REPL16;   // 16-bit entries: next << NSH | rare, next << NSH = next * stride
+                                                                        // (else next << 16 | next * stride | rare)
+    constexpr uint32_t NSH = TM == (int)TABLE_REPL16 ? 6u : E16 ? 1u : 16u;   // entry >> NSH = the state
+    constexpr uint32_t EMASK = TM == (int)TABLE_REPL16 ? 0xFFC0u : 0xFFFEu;   // 16-bit entries: the bits of next * stride
+    constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_REPL16 ? 64u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
+    constexpr uint32_t cstride = REPL ? 128u : 4u;                        // class-table entry stride
+    const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : TM == (int)TABLE_REPL16 ? (uint32_t)lane * 2u : 0u;
+    const uint32_t claneoff = REPL ? (uint32_t)lane * 4u : 0u;            // the class table holds 32-bit entries in either case
 
     // ---- stage the tables ----------------------------------------------------------------------------------------------
     if (SMEM_TAB) {
-        constexpr uint32_t csh = TM == (int)TABLE_REPL ? 5u : 0u;   // log2(copies)
+        constexpr uint32_t csh = REPL ? 5u : 0u;   // log2(copies)
 #pragma unroll
         // (four global loads per thread in flight, then their stores: the shared-memory stores are compiler barriers, and a loop of
         //  load -> store round trips made the prologue of a one-string launch 100 us long)
@@ -181,8 +185,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                     const uint32_t idx = i >> csh, l = i & ((1u << csh) - 1u), e = ev[u];
                     // single-copy tables: row k is XOR-swizzled by its class (walk_swizzle) — lanes in the same state with
                     // different classes would otherwise all hit one bank (the row size is a power of two)
-                    const uint32_t swz = TM == (int)TABLE_REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
-                    if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
+                    const uint32_t swz = REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
+                    if (TM == (int)TABLE_REPL16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + idx * 64 + l * 2), "h"((unsigned short)(((e >> 16) << 6) | (e & 1u))) : "memory");
+                    else if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
                     else sts32(t0 + ((idx * stride) ^ swz) + l * 4, e | ((e >> 16) * stride));
                 }
             }
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 uint32_t v;
                 if (D == 1) {
                     const uint32_t k = kv4[u][0], rb = p.def[0].padded_states * stride;
-                    v = base_s + lay.tab[0] + k * rb + l * 4 + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rb));
+                    v = base_s + lay.tab[0] + k * rb + (TM == (int)TABLE_REPL16 ? l * 2 : l * 4) + (REPL ? 0u : walk_swizzle(k, rb));
                 } else {
                     v = 0;
 #pragma unroll
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     const uint32_t Mpad = (M + 15u) & ~15u;                             // rows written (row_pitch >= Mpad by contract)
     const uint32_t n_chunks = (Mpad + DCH - 1) / DCH;
     const uint64_t rp = p.row_pitch;
-    const uint32_t cls_lane_s = base_s + lay.cls + laneoff;
+    const uint32_t cls_lane_s = base_s + lay.cls + claneoff;
     uint32_t tabl[D], rowb[D], hist_s[D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
@@ -268,10 +273,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             if (D == 1) row = cent;
             else {
                 const uint32_t k = (cent >> (8 * d)) & 0xFFu;
-                row = tabl[d] + k * rowb[d] + (TM == (int)TABLE_REPL ? 0u : walk_swizzle(k, rowb[d]));
+                row = tabl[d] + k * rowb[d] + (REPL ? 0u : walk_swizzle(k, rowb[d]));
             }
             // XOR, not OR: the low bits of `row` of a single-copy table carry the class swizzle (they are zero otherwise)
-            if (E16) { uint32_t e; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((cur & 0xFFFEu) ^ row)); return e; }
+            if (E16) { uint32_t e; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((cur & EMASK) ^ row)); return e; }
             return lds32((cur & 0xFFFCu) ^ row);
         } else {
             const uint32_t k = __ldg(p.def[d].byte_class + c);
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t f = (p.def[d].init_states && valid) ? (uint32_t)p.def[d].init_states[idx] : p.def[d].first_state;
-            cur[d] = E16 ? (f << 1) : (f << 16) | (f * stride);
+            cur[d] = E16 ? (f << NSH) : (f << 16) | (f * stride);
         }
 
         // staging geometry
@@ -477,11 +482,11 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         for (int d = 0; d < D; d++) {
                             acc |= before[d][1] | before[d][2];           // entries of rows 4q, 4q+1 (3-input LOP3s)
                             acc |= before[d][3] | cur[d];                 // rows 4q+2, 4q+3
-                            if (E16) {                                    // 16-bit entries: the state is entry >> 1
-                                if (SB == 1) pk[d][q] = (before[d][0] >> 1) | ((before[d][1] >> 1) << 8) | ((before[d][2] >> 1) << 16) | ((before[d][3] >> 1) << 24);
+                            if (E16) {                                    // 16-bit entries: the state is entry >> NSH
+                                if (SB == 1) pk[d][q] = (before[d][0] >> NSH) | ((before[d][1] >> NSH) << 8) | ((before[d][2] >> NSH) << 16) | ((before[d][3] >> NSH) << 24);
                                 else {
-                                    pk[d][q * 2] = (before[d][0] >> 1) | ((before[d][1] >> 1) << 16);
-                                    pk[d][q * 2 + 1] = (before[d][2] >> 1) | ((before[d][3] >> 1) << 16);
+                                    pk[d][q * 2] = (before[d][0] >> NSH) | ((before[d][1] >> NSH) << 16);
+                                    pk[d][q * 2 + 1] = (before[d][2] >> NSH) | ((before[d][3] >> NSH) << 16);
                                 }
                             } else if (SB == 1) {                         // state bytes (entry byte 2) of four rows into one word
                                 const uint32_t lo = prmt(before[d][0], before[d][1], 0x4462u), hi = prmt(before[d][2], before[d][3], 0x4462u);

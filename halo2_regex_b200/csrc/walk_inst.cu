@@ -32,6 +32,7 @@ int launch_walk_d<B2R_INST_D>(const WalkParams& p, bool wide, size_t smem, int g
         if (shist) { set_error("walk_kernel: shared-memory bins with 2-byte states"); return B2R_ERR_UNSUPPORTED; }
         switch (tm) {
             case TABLE_REPL: return launch_walk_one<D, uint16_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+            case TABLE_REPL16: return launch_walk_one<D, uint16_t, TABLE_REPL16, HIST_GLOBAL>(p, smem, grid, block, st);
             case TABLE_PLAIN: return launch_walk_one<D, uint16_t, TABLE_PLAIN, HIST_GLOBAL>(p, smem, grid, block, st);
             case TABLE_PLAIN16: return launch_walk_one<D, uint16_t, TABLE_PLAIN16, HIST_GLOBAL>(p, smem, grid, block, st);
             default: return launch_walk_one<D, uint16_t, TABLE_GLOBAL, HIST_GLOBAL>(p, smem, grid, block, st);
@@ -44,6 +45,9 @@ int launch_walk_d<B2R_INST_D>(const WalkParams& p, bool wide, size_t smem, int g
     if (tm == TABLE_REPL)
         return shist ? launch_walk_one<D, uint8_t, TABLE_REPL, HIST_SMEM>(p, smem, grid, block, st)
                      : launch_walk_one<D, uint8_t, TABLE_REPL, HIST_GLOBAL>(p, smem, grid, block, st);
+    if (tm == TABLE_REPL16)
+        return shist ? launch_walk_one<D, uint8_t, TABLE_REPL16, HIST_SMEM>(p, smem, grid, block, st)
+                     : launch_walk_one<D, uint8_t, TABLE_REPL16, HIST_GLOBAL>(p, smem, grid, block, st);
     if (tm == TABLE_PLAIN16)
         return shist ? launch_walk_one<D, uint8_t, TABLE_PLAIN16, HIST_SMEM>(p, smem, grid, block, st)
                      : launch_walk_one<D, uint8_t, TABLE_PLAIN16, HIST_GLOBAL>(p, smem, grid, block, st);

@@ -343,7 +343,7 @@ class RegexVerifyConfig:
         """(table placement, bin placement) chosen by the last call: see b2r_last_plan in include/b2r.h."""
         t, h = C.c_uint32(), C.c_uint32()
         _raise(lib.b2r_last_plan(self._h, C.byref(t), C.byref(h)))
-        return ("repl", "plain", "global", "plain16")[t.value], ("none", "smem", "global")[h.value]
+        return ("repl", "plain", "global", "plain16", "repl16")[t.value], ("none", "smem", "global")[h.value]
 
     # ---- match_substrs (src/lib.rs:311-773): one string ------------------------------------------------------------
     def match_substrs(self, characters, ctx=None):

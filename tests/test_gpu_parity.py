@@ -228,7 +228,8 @@ def test_device_pointer_entry_point():
     assert H.compare_outputs(out.to_host(), o) == []
 
 
-@pytest.mark.parametrize("table_mode,hist_mode", [("repl", "smem"), ("plain", "smem"), ("plain16", "smem"), ("repl", "global"), ("plain16", "global"), ("global", "global")])
+@pytest.mark.parametrize("table_mode,hist_mode", [("repl", "smem"), ("plain", "smem"), ("plain16", "smem"), ("repl", "global"), ("plain16", "global"), ("global", "global"),
+                                                  ("repl16", "smem"), ("repl16", "global")])
 @pytest.mark.parametrize("set_name", ["regex1", "three"])
 def test_table_and_bin_placements(monkeypatch, set_name, table_mode, hist_mode):
     """Every placement of the walk tables (bank-replicated / single copy in shared memory, global) and of the
