@@ -121,8 +121,15 @@ int b2r_config_new_multi(const b2r_allstr* const* allstr, const b2r_substr* cons
                          const uint32_t* n_substrs, uint32_t n_defs, uint64_t max_chars_size, const int* device_ids,
                          uint32_t n_devices, b2r_config** out);
 uint32_t b2r_config_num_devices(const b2r_config*);
-/* testing / tuning knobs of a handle, the same ones the B2R_* environment variables set when it is created
- * ("table_mode", "hist_mode", "fuse", "slices", "host_threads", "small_path", ...) */
+/* testing / tuning knobs of a handle, the same ones the B2R_* environment variables set when it is created (none is needed in
+ * production; results are bit-identical under every setting):
+ *   table_mode   repl | repl16 | plain | plain16 | global   placement of the walk tables (default: chosen by shared-memory budget)
+ *   hist_mode    smem | global                              placement of the multiplicity bins
+ *   fuse         1 | 2 | 0 | -1    emit stage inside walk_kernel / own kernel after a walk that zero-fills / own kernel that zero-fills too /
+ *                                  default (1 for one def with replicated tables, else 2)
+ *   stagger_ns   start offset between the warps of a walk CTA (-1: default)
+ *   slices, host_threads, small_path, sparse_cap, sparse_direct, trace_host   host entry points (b2r_match_batch_host)
+ *   hist_cache_log2, spread_fill, long_fused, debug, host_debug               kernel tuning / timing experiments */
 int b2r_config_set_option(b2r_config*, const char* name, const char* value);
 
 /* Page-locked host memory for the buffers handed to the host-pointer entry points (a copy into pageable memory cannot overlap
