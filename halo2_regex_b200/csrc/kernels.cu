@@ -60,7 +60,24 @@ static constexpr int MIN_WARPS_REPL = 12;  // below this the replicated tables a
 
 // Picks where the walk tables and the multiplicity bins live.  Preference: replicated tables + shared bins with as many
 // warps as possible; then a single copy of the tables; then global tables.  Bins go to shared memory whenever they fit.
+static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode, int hist_cache_log2);
+
 int plan_walk(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode, int hist_cache_log2) {
+    p.cls_repl = 0;
+    int rc = plan_walk_tables(p, wide, force_table_mode, force_hist_mode, hist_cache_log2);
+    if (rc) return rc;
+    // single-copy tables in shared memory: the byte -> class lookup (one per byte, shared by all defs) is still made conflict-free by
+    // replicating the 256-entry class table once per lane (32 KB) — when every warp still fits next to it
+    if ((p.table_mode == TABLE_PLAIN || p.table_mode == TABLE_PLAIN16) && p.n_tiles > 8) {
+        int n_sm = 0, max_smem = 0;
+        if ((rc = device_limits(&n_sm, &max_smem))) return rc;
+        p.cls_repl = 1;
+        if (walk_smem_bytes(p, wide ? 2 : 1, WALK_MAX_THREADS / 32) > (size_t)max_smem) p.cls_repl = 0;
+    }
+    return B2R_OK;
+}
+
+static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int force_hist_mode, int hist_cache_log2) {
     int n_sm = 0, max_smem = 0;
     int rc = device_limits(&n_sm, &max_smem);
     if (rc) return rc;

@@ -70,6 +70,7 @@ struct WalkParams {
     uint32_t* fmask;
     uint32_t fm_words;
     uint32_t table_mode;             // TABLE_REPL / TABLE_REPL16 / TABLE_PLAIN / TABLE_PLAIN16 / TABLE_GLOBAL (walk.cuh)
+    uint32_t cls_repl;               // single-copy tables: the byte -> class table is still replicated once per lane (32 KB) when that costs no warp
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t hist_cache_log2;        // HIST_GLOBAL: log2 of the slots of the per-def shared-memory bin cache in front of L2
     uint32_t ep_smem_bytes;          // bytes of shared memory for the endpoint counters (0: count with global atomics)

@@ -78,7 +78,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // in-row XOR swizzle of class row k of a single-copy table (row_bytes = padded_states * stride, a power of two): words
 __host__ __device__ inline uint32_t walk_swizzle(uint32_t k, uint32_t row_bytes) { return (k << 2) & (row_bytes - 1u) & 0x7Cu; }
 __host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return table_mode == TABLE_REPL ? 128u : table_mode == TABLE_REPL16 ? 64u : table_mode == TABLE_PLAIN16 ? 2u : 4u; }
-__host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode) { return table_mode == TABLE_REPL || table_mode == TABLE_REPL16 ? 128u : 4u; }
+__host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode, uint32_t cls_repl) { return table_mode == TABLE_REPL || table_mode == TABLE_REPL16 || cls_repl ? 128u : 4u; }
 __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
 struct WalkLayout {
@@ -105,7 +105,7 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
         }
         cur = walk_align_up(cur, 128);
         L.cls = cur;
-        cur += 256 * walk_cls_stride(p.table_mode);
+        cur += 256 * walk_cls_stride(p.table_mode, p.cls_repl);
     }
     if (p.hist_mode == HIST_SMEM)
         for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     constexpr uint32_t NSH = TM == (int)TABLE_REPL16 ? 6u : E16 ? 1u : 16u;   // entry >> NSH = the state
     constexpr uint32_t EMASK = TM == (int)TABLE_REPL16 ? 0xFFC0u : 0xFFFEu;   // 16-bit entries: the bits of next * stride
     constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_REPL16 ? 64u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
-    constexpr uint32_t cstride = REPL ? 128u : 4u;                        // class-table entry stride
+    const uint32_t cstride = REPL ? 128u : (p.cls_repl ? 128u : 4u);      // class-table entry stride (a constant for replicated tables)
     const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : TM == (int)TABLE_REPL16 ? (uint32_t)lane * 2u : 0u;
-    const uint32_t claneoff = REPL ? (uint32_t)lane * 4u : 0u;            // the class table holds 32-bit entries in either case
+    const uint32_t claneoff = (REPL || p.cls_repl) ? (uint32_t)lane * 4u : 0u;   // the class table holds 32-bit entries in either case
 
     // ---- stage the tables ----------------------------------------------------------------------------------------------
     if (SMEM_TAB) {
@@ -192,23 +192,24 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 }
             }
         }
-        for (uint32_t i0 = threadIdx.x; i0 < (256u << csh); i0 += SU * blockDim.x) {
+        const uint32_t ccsh = (REPL || p.cls_repl) ? 5u : 0u;             // log2(copies) of the class table
+        for (uint32_t i0 = threadIdx.x; i0 < (256u << ccsh); i0 += SU * blockDim.x) {
             uint32_t kv4[SU][D];
 #pragma unroll
             for (int u = 0; u < SU; u++) {
                 const uint32_t i = i0 + u * blockDim.x;
 #pragma unroll
-                for (int d = 0; d < D; d++) kv4[u][d] = i < (256u << csh) ? (uint32_t)__ldg(p.def[d].byte_class + (i >> csh)) : 0u;
+                for (int d = 0; d < D; d++) kv4[u][d] = i < (256u << ccsh) ? (uint32_t)__ldg(p.def[d].byte_class + (i >> ccsh)) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < SU; u++) {
                 const uint32_t i = i0 + u * blockDim.x;
-                if (i >= (256u << csh)) break;
-                const uint32_t c = i >> csh, l = i & ((1u << csh) - 1u);
+                if (i >= (256u << ccsh)) break;
+                const uint32_t c = i >> ccsh, l = i & ((1u << ccsh) - 1u);
                 uint32_t v;
                 if (D == 1) {
                     const uint32_t k = kv4[u][0], rb = p.def[0].padded_states * stride;
-                    v = base_s + lay.tab[0] + k * rb + (TM == (int)TABLE_REPL16 ? l * 2 : l * 4) + (REPL ? 0u : walk_swizzle(k, rb));
+                    v = base_s + lay.tab[0] + k * rb + (TM == (int)TABLE_REPL16 ? l * 2 : TM == (int)TABLE_REPL ? l * 4 : 0u) + (REPL ? 0u : walk_swizzle(k, rb));
                 } else {
                     v = 0;
 #pragma unroll
