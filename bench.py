@@ -642,10 +642,13 @@ def main():
                "sample": f"first 2^16 of the 2^{args.log2_strings} strings (64 MiB), all witness columns + multiplicities, {dt:.1f} s",
                "note": "C restatement of src/lib.rs:311-888 (hash-map walk, scans) without halo2 cell assignment / field inversions: faster than the real reference"}
 
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same workload (newest round)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "walk_kernel_traffic.json")) as f:
-            tj = json.load(f)
+        import glob
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_walk_kernel_traffic.json"))):
+            with open(path) as f:
+                tj = json.load(f)
             if tj.get("log2_strings") == args.log2_strings:
                 traffic = tj["dram_bytes_per_launch"]
     except Exception:
