@@ -254,6 +254,15 @@ def test_emit_stage_fused_and_separate(monkeypatch, set_name, fuse):
     assert cfg.last_launch_count() == (2 if fuse == 1 else 3)
 
 
+def test_offset_warp_starts(monkeypatch):
+    """B2R_STAGGER_NS: the warps of a walk CTA start at different times (the default only does this on large batches)."""
+    monkeypatch.setenv("B2R_STAGGER_NS", "2000")
+    rng = random.Random(5)
+    strings = _random_strings(rng, 700, 200, SNIPPETS)
+    _both("regex1", 201, strings)
+    _both("three", 201, strings)
+
+
 def test_default_emit_placement():
     rng = random.Random(11)
     strings = _random_strings(rng, 200, 120, SNIPPETS)
