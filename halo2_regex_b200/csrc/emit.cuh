@@ -138,12 +138,31 @@ static __device__ __noinline__ uint2 emit_segment(const WalkParams& p, const Emi
     return make_uint2(n_rec, n_cmp + (b - a));
 }
 
-// 16 rows of one string in registers: the bytes and the states of every def
-template <int D, typename ST>
+// 16 rows of one string in registers: the bytes and the states of every def.
+// SG (the stand-alone emit kernel): the granule is mirrored in a shared-memory scratch of the thread (vector v at gs + v * EMIT_SG_PITCH:
+// the bytes, then the states of every def), so that a row chosen at run time costs one LDS instead of a chain of selects — the per-row
+// loops of the scan are what that kernel spends its instructions on.
+constexpr uint32_t EMIT_SG_PITCH = 256 * 16;   // EMIT_THREADS * 16 bytes: vector v of thread t lives at v * pitch + t * 16
+template <int D, typename ST, bool SG = false>
 struct Granule {
     uint32_t w[4];
     uint32_t sv[D][4 * sizeof(ST)];
     uint32_t n;                    // rows that are characters (1..16)
+    uint32_t gs;                   // SG: shared-memory address of this thread's vector 0
+
+    __device__ __forceinline__ void mirror() {
+        if (!SG) return;
+        auto sts = [](uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t q) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(q) : "memory"); };
+        sts(gs, w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            sts(gs + (1 + d * (int)sizeof(ST)) * EMIT_SG_PITCH, sv[d][0], sv[d][1], sv[d][2], sv[d][3]);
+            if (sizeof(ST) == 2) {
+                constexpr int H = 4 * (sizeof(ST) - 1);
+                sts(gs + (2 + d * (int)sizeof(ST)) * EMIT_SG_PITCH, sv[d][H], sv[d][H + 1], sv[d][H + 2], sv[d][H + 3]);
+            }
+        }
+    }
 
     // granule g of string j (src = its first byte, L its length); 16*g < L
     // stash_g / stash_s: a granule of this string kept in shared memory by the walk (fused mode): vector v at stash_s + 512*v,
@@ -161,6 +180,7 @@ struct Granule {
                 sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
                 if (sizeof(ST) == 2) { const uint4 b2 = lds(stash_s + (2 + d * sizeof(ST)) * 512); sv[d][4 * (sizeof(ST) - 1)] = b2.x; sv[d][4 * (sizeof(ST) - 1) + 1] = b2.y; sv[d][4 * (sizeof(ST) - 1) + 2] = b2.z; sv[d][4 * (sizeof(ST) - 1) + 3] = b2.w; }
             }
+            mirror();
             return;
         }
         // 16 bytes from an arbitrary address: two aligned 16-byte loads shifted into place; the second one is only
@@ -186,6 +206,7 @@ struct Granule {
             sv[d][0] = a.x; sv[d][1] = a.y; sv[d][2] = a.z; sv[d][3] = a.w;
             if (sizeof(ST) == 2) { const uint4 b2 = __ldcg(sp + 1); sv[d][4 * (sizeof(ST) - 1)] = b2.x; sv[d][4 * (sizeof(ST) - 1) + 1] = b2.y; sv[d][4 * (sizeof(ST) - 1) + 2] = b2.z; sv[d][4 * (sizeof(ST) - 1) + 3] = b2.w; }
         }
+        mirror();
     }
     // compile-time row index
     __device__ __forceinline__ uint32_t byte_at(int r) const { return (w[r >> 2] >> (8 * (r & 3))) & 0xFFu; }
@@ -194,10 +215,17 @@ struct Granule {
     }
     // run-time row index
     __device__ __forceinline__ uint32_t byte_dyn(uint32_t r) const {
+        if (SG) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(gs + r)); return v; }
         const uint32_t q = r < 8 ? (r < 4 ? w[0] : w[1]) : (r < 12 ? w[2] : w[3]);
         return (q >> (8 * (r & 3))) & 0xFFu;
     }
     __device__ __forceinline__ uint32_t state_dyn(int d, uint32_t r) const {
+        if (SG) {
+            uint32_t v;
+            if (sizeof(ST) == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(gs + (1 + d) * EMIT_SG_PITCH + r));
+            else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(gs + (1 + 2 * d + (r >> 3)) * EMIT_SG_PITCH + (r & 7u) * 2u));
+            return v;
+        }
         if (sizeof(ST) == 1) {
             const uint32_t q = r < 8 ? (r < 4 ? sv[d][0] : sv[d][1]) : (r < 12 ? sv[d][2] : sv[d][3]);
             return (q >> (8 * (r & 3))) & 0xFFu;
@@ -210,7 +238,7 @@ struct Granule {
 };
 
 // The string a lane works on, and what the scan learns about it.
-template <int D, typename ST>
+template <int D, typename ST, bool SG = false>
 struct LaneString {
     const WalkParams& p;
     const EmitTables<D>& tb;
@@ -218,6 +246,7 @@ struct LaneString {
     const uint8_t* src;
     uint32_t L;
     uint32_t stash_g, stash_s;  // granule kept in shared memory by the walk (fused mode), NO_POS = none
+    uint32_t gs = 0;            // SG: this thread's granule scratch (Granule::gs)
     // results of the scan
     uint32_t seg_a[EMIT_NSEG], seg_b[EMIT_NSEG], n_seg;   // masked segments [a,b), in order; n_seg may exceed EMIT_NSEG
     uint32_t n_rec, n_cmp;
@@ -281,7 +310,8 @@ struct LaneString {
     // flagged granule g; partner_flagged: the other granule of its 32-row window is flagged too (and writes itself)
     template <bool PATCH>
     __device__ __forceinline__ void scan_granule(uint32_t g, bool partner_flagged) {
-        Granule<D, ST> gr;
+        Granule<D, ST, SG> gr;
+        gr.gs = gs;
         gr.load(p, j, src, L, g, stash_g, stash_s);
         // pass 1, unrolled, all lanes in step: rows whose state can start a transition with a substr id (or is the trap state)
         uint32_t hot = 0;
@@ -421,7 +451,8 @@ struct LaneString {
             const uint32_t a = seg_a[k], b = seg_b[k];
             for (uint32_t g = a >> 4; g <= (b - 1) >> 4; g++) {
                 if ((g >> 1) != cur_t) { flush(); cur_t = g >> 1; }
-                Granule<D, ST> gr;
+                Granule<D, ST, SG> gr;
+                gr.gs = gs;
                 gr.load(p, j, src, L, g, stash_g, stash_s);
                 const uint32_t lo = a > 16 * g ? a - 16 * g : 0u, hi = b < 16 * g + 16 ? b - 16 * g : 16u;
                 for (uint32_t r = lo; r < hi; r++) {
@@ -452,11 +483,12 @@ struct LaneString {
 };
 
 // Warp-cooperative emitter for one tile of 32 consecutive strings.
-template <int D, typename ST>
+template <int D, typename ST, bool SG = false>
 struct TileEmitter {
     const WalkParams& p;
     const EmitTables<D>& tb;
     const int lane;
+    uint32_t gs = 0;            // SG: this thread's granule scratch in shared memory
 
     __device__ __forceinline__ TileEmitter(const WalkParams& p_, const EmitTables<D>& tb_, int lane_) : p(p_), tb(tb_), lane(lane_) {}
 
@@ -487,8 +519,8 @@ struct TileEmitter {
         // ---- scan + masks (lane = string) ---------------------------------------------------------------------------------
         uint32_t r_nrec = 0, r_ncmp = 0, r_flags = 0;
         bool patch = false;
-        LaneString<D, ST> ls(p, tb, jl, p.bytes + off, Ll);
-        ls.stash_g = stash_g; ls.stash_s = stash_s;
+        LaneString<D, ST, SG> ls(p, tb, jl, p.bytes + off, Ll);
+        ls.stash_g = stash_g; ls.stash_s = stash_s; ls.gs = gs;
         if (live && !(p.debug & 2) && (p.fm_words > 2 || (fw0 | fw1) != 0)) {
             ls.template scan<false>(fw0, fw1, p.fmask);
             if (ls.invalid) r_flags = B2R_ST_INVALID_TRANSITION;
@@ -564,6 +596,8 @@ __host__ __device__ inline uint32_t emit_smem_bytes(const WalkParams& p) {
         for (uint32_t d = 0; d < p.n_defs; d++) n += ((p.def[d].num_classes * p.def[d].num_states * 4u + 256u) + 15u) & ~15u;
     return n;
 }
+// the stand-alone emit kernel appends the granule scratch of its threads (Granule<.., SG = true>) behind the tables
+__host__ __device__ inline uint32_t emit_scratch_bytes(const WalkParams& p, uint32_t state_bytes) { return (1u + p.n_defs * state_bytes) * EMIT_SG_PITCH; }
 // Every thread of the CTA calls this, followed by a __syncthreads().
 template <int D>
 __device__ __forceinline__ void emit_tables_init(const WalkParams& p, unsigned char* esmem, EmitTables<D>& tb) {
@@ -663,7 +697,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
     __syncthreads();
     const uint32_t zero_s = (uint32_t)__cvta_generic_to_shared(zero_buf);
 
-    TileEmitter<D, ST> em(p, tb, lane);
+    TileEmitter<D, ST, true> em(p, tb, lane);
+    em.gs = (uint32_t)__cvta_generic_to_shared(esmem) + ((emit_smem_bytes(p) + 15u) & ~15u) + threadIdx.x * 16u;
     EmitTotals tot;
     auto fetch = [&]() -> unsigned long long {
         unsigned long long t = 0;

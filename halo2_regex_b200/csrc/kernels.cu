@@ -181,7 +181,7 @@ int launch_emit(const WalkParams& p, bool wide, void* stream, LaunchInfo* chosen
     int n_sm = 0, max_smem = 0;
     int rc = device_limits(&n_sm, &max_smem);
     if (rc) return rc;
-    const size_t smem = emit_smem_bytes(p);
+    const size_t smem = ((emit_smem_bytes(p) + 15u) & ~15u) + emit_scratch_bytes(p, wide ? 2 : 1);   // tables + endpoint counters, granule scratch
     const int wpc = EMIT_THREADS / 32;
     int per_sm = 2048 / EMIT_THREADS;
     { const int by_smem = (int)((size_t)max_smem / (smem + EMIT_ZERO_BYTES + 1024)); if (by_smem < per_sm) per_sm = by_smem < 1 ? 1 : by_smem; }   // + the static zero buffer
