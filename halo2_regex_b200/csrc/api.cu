@@ -25,6 +25,7 @@ int upload_tables(b2r_config* c) {
         total += align_up(256, 256) + align_up(pd.trans.size() * 4, 256) + align_up(pd.row_bin.size() * 4, 256) +
                  2 * align_up(pd.erows.size() * 4, 256) + align_up((size_t)pd.num_classes * padded_states(pd.num_states) * 4, 256);
     }
+    total += 512;                                                          // the two byte <-> bin column maps
     CUDA_TRY(cudaMalloc(&c->tables, total));
     unsigned char* base = (unsigned char*)c->tables;
     size_t off = 0;
@@ -49,6 +50,29 @@ int upload_tables(b2r_config* c) {
         c->dev[d].erow_start_bin = (uint32_t*)put(pd.erow_start_bin.data(), pd.erows.size() * 4);
         c->dev[d].erow_end_bin = (uint32_t*)put(pd.erow_end_bin.data(), pd.erows.size() * 4);
         scratch += align_up((size_t)256 * pd.num_states * 8, 256) + 2 * align_up((size_t)std::max<uint32_t>(pd.num_substrs, 1) * pd.num_states * 8, 256);
+    }
+    {   // compact bins: a column for every byte that some def has a transition for, one more for all the others
+        uint8_t of_byte[256], byte_of[256];
+        uint32_t nb = 0;
+        for (int ch = 0; ch < 256; ch++) {
+            bool any = false;
+            for (uint32_t d = 0; d < c->n_defs && !any; d++) {
+                const PackedDef& pd = c->packed[d];
+                const uint32_t k = pd.byte_class[ch];
+                for (uint32_t st2 = 0; st2 < pd.num_states && !any; st2++) any = !(pd.trans[(size_t)k * pd.num_states + st2] & ENT_INVALID);
+            }
+            of_byte[ch] = any ? (uint8_t)nb : 0xFF;
+            if (any) byte_of[nb++] = (uint8_t)ch;
+        }
+        if (nb < 255) {
+            for (int ch = 0; ch < 256; ch++) if (of_byte[ch] == 0xFF) of_byte[ch] = (uint8_t)nb;   // the column nobody reads back
+            c->bin_cols = nb + 1;
+        } else {   // (nearly) every byte is in use: dense bins, column = byte
+            for (int ch = 0; ch < 256; ch++) { of_byte[ch] = (uint8_t)ch; byte_of[ch] = (uint8_t)ch; }
+            c->bin_cols = 256;
+        }
+        c->d_bin_of_byte = (uint8_t*)put(of_byte, 256);
+        c->d_bin_byte = (uint8_t*)put(byte_of, 256);
     }
     if (put_err != cudaSuccess) { set_error("uploading the packed tables failed: %s", cudaGetErrorString(put_err)); return B2R_ERR_CUDA; }
     CUDA_TRY(cudaGetLastError());
@@ -123,6 +147,7 @@ void fill_walk_params(const b2r_config* c, WalkParams& p, const uint8_t* d_bytes
         dd.hist = c->dev[d].hist; dd.ep_start = c->dev[d].ep_start; dd.ep_end = c->dev[d].ep_end;
         dd.states = o->states[d]; dd.substr_ids = o->substr_ids[d]; dd.start_enable = o->start_enable[d]; dd.end_enable = o->end_enable[d];
     }
+    p.bin_cols = c->bin_cols; p.bin_of_byte = c->d_bin_of_byte; p.bin_byte = c->d_bin_byte;
     p.masked_chars = o->masked_chars; p.masked_substr_ids = o->masked_substr_ids;
     p.status = o->status; p.records = o->records; p.compact_bytes = o->compact_bytes;
     p.max_records = o->records ? o->max_records : 0; p.compact_pitch = o->compact_bytes ? o->compact_pitch : 0;

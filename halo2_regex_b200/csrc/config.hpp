@@ -121,6 +121,9 @@ struct b2r_config {
     b2r::PackedDef packed[B2R_MAX_DEFS];
     b2r::DevDef dev[B2R_MAX_DEFS];
     void* tables = nullptr;      // one allocation holding every constant table
+    uint8_t* d_bin_of_byte = nullptr;   // compact multiplicity bins (kernels.cuh): byte -> column, column -> byte; inside `tables`
+    uint8_t* d_bin_byte = nullptr;
+    uint32_t bin_cols = 256;
     void* scratch = nullptr;     // BatchCounters + hist + endpoint counters, zeroed per batch
     size_t scratch_bytes = 0;
     b2r_batch_status* d_batch_status = nullptr;

@@ -56,6 +56,7 @@ int device_limits(int* n_sm, int* max_smem) {
     return B2R_OK;
 }
 
+static constexpr int MIN_WARPS_REPL16 = 10; // 16-bit replicated tables: taken when at least this many warps fit next to them
 static constexpr int MIN_WARPS_REPL = 12;  // below this the replicated tables are not worth the lost occupancy (measured on the two-def set)
 
 // Picks where the walk tables and the multiplicity bins live.  Preference: replicated tables + shared bins with as many
@@ -90,7 +91,7 @@ static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int 
                 if ((uint64_t)p.def[d].padded_states * stride > 65536u) return false;   // the entry's low bits hold next*stride
         }
         uint64_t bins = 0;
-        for (uint32_t d = 0; d < p.n_defs; d++) bins += (uint64_t)(p.def[d].num_states + 1) * 1024u;
+        for (uint32_t d = 0; d < p.n_defs; d++) bins += (uint64_t)(p.def[d].num_states + 1) * walk_bin_cols(p) * 4u;
         if (hm == HIST_SMEM && (wide || bins > (uint64_t)max_smem)) return false;
         uint64_t tabs = 0;
         if (tm != TABLE_GLOBAL)
@@ -119,6 +120,11 @@ static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int 
     if (p.n_tiles <= 8 && force_table_mode < 0 && force_hist_mode < 0 && !p.segment_mode)
         for (const uint32_t tm : {P32, P16})
             if (fits(tm, HIST_SMEM, 4)) return B2R_OK;
+    // two or three small DFAs whose 32-bit replicated tables do not fit: 16-bit replicated tables next to compact bins, if enough warps
+    // still fit to hide the latency of the chains
+    if (force_table_mode < 0 && force_hist_mode < 0 && p.n_defs >= 2 && p.n_defs <= 3 && !wide && !fits(TABLE_REPL, HIST_SMEM, 4) &&
+        fits(TABLE_REPL16, HIST_SMEM, MIN_WARPS_REPL16))
+        return B2R_OK;
     for (const auto& o : order) {
         if (force_table_mode >= 0 && (uint32_t)force_table_mode != o[0]) continue;   // testing hooks: honoured when they fit
         if (force_hist_mode >= 0 && (uint32_t)force_hist_mode != o[1]) continue;

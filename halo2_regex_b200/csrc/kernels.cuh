@@ -70,6 +70,11 @@ struct WalkParams {
     uint32_t* fmask;
     uint32_t fm_words;
     uint32_t table_mode;             // TABLE_REPL / TABLE_REPL16 / TABLE_PLAIN / TABLE_PLAIN16 / TABLE_GLOBAL (walk.cuh)
+    // two or three defs on 16-bit tables with shared-memory bins: the bins have one column per byte that SOME def can read (bin_cols - 1
+    // of them, plus one column for every other byte) instead of 256; the column of a byte rides in the spare byte of the class-table entry
+    uint32_t bin_cols;               // columns of the compact bins (<= 256)
+    const uint8_t* bin_of_byte;      // [256] byte -> column (device)
+    const uint8_t* bin_byte;         // [bin_cols - 1] column -> byte (device)
     uint32_t cls_repl;               // single-copy tables: the byte -> class table is still replicated once per lane (32 KB) when that costs no warp
     uint32_t hist_mode;              // HIST_NONE / HIST_SMEM / HIST_GLOBAL
     uint32_t hist_cache_log2;        // HIST_GLOBAL: log2 of the slots of the per-def shared-memory bin cache in front of L2

@@ -81,6 +81,12 @@ __host__ __device__ inline uint32_t walk_stride(uint32_t table_mode) { return ta
 __host__ __device__ inline uint32_t walk_cls_stride(uint32_t table_mode, uint32_t cls_repl) { return table_mode == TABLE_REPL || table_mode == TABLE_REPL16 || cls_repl ? 128u : 4u; }
 __host__ __device__ inline uint32_t walk_align_up(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
+// columns of a def's shared-memory bins: the compact layout (kernels.cuh, bin_cols) for two or three defs on 16-bit tables, else one per byte
+__host__ __device__ inline uint32_t walk_bin_cols(const WalkParams& p) {
+    const bool e16 = p.table_mode == TABLE_PLAIN16 || p.table_mode == TABLE_REPL16;
+    return (e16 && p.hist_mode == HIST_SMEM && p.n_defs >= 2 && p.n_defs <= 3 && p.bin_cols && p.bin_cols < 256) ? p.bin_cols : 256u;
+}
+
 struct WalkLayout {
     uint32_t tab[B2R_MAX_DEFS];    // byte offsets from the aligned base; table rows are P*stride bytes and aligned to that
     uint32_t cls;                  // 256 entries of `stride` bytes
@@ -108,7 +114,7 @@ __host__ __device__ inline WalkLayout walk_layout(const WalkParams& p, uint32_t 
         cur += 256 * walk_cls_stride(p.table_mode, p.cls_repl);
     }
     if (p.hist_mode == HIST_SMEM)
-        for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * 1024u; }
+        for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += (p.def[d].num_states + 1) * walk_bin_cols(p) * 4u; }
     if (p.hist_mode == HIST_GLOBAL)   // bin cache: 2^log2 slots of {key, count}
         for (uint32_t d = 0; d < p.n_defs; d++) { L.hist[d] = cur; cur += 8u << p.hist_cache_log2; }
     cur = walk_align_up(cur, 16);
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     const uint32_t cstride = REPL ? 128u : (p.cls_repl ? 128u : 4u);      // class-table entry stride (a constant for replicated tables)
     const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : TM == (int)TABLE_REPL16 ? (uint32_t)lane * 2u : 0u;
     const uint32_t claneoff = (REPL || p.cls_repl) ? (uint32_t)lane * 4u : 0u;   // the class table holds 32-bit entries in either case
+    constexpr bool CBINS = E16 && HM == (int)HIST_SMEM && D >= 2 && D <= 3;   // compact bins possible (walk_bin_cols decides)
+    const uint32_t bcols = walk_bin_cols(p);
 
     // ---- stage the tables ----------------------------------------------------------------------------------------------
     if (SMEM_TAB) {
@@ -214,6 +222,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                     v = 0;
 #pragma unroll
                     for (int d = 0; d < D; d++) v |= kv4[u][d] << (8 * d);
+                    if (CBINS) v |= (bcols < 256u ? (uint32_t)__ldg(p.bin_of_byte + c) : c) << 24;   // the bin column of the byte
                 }
                 sts32(base_s + lay.cls + c * cstride + l * 4, v);
             }
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     if (HM == (int)HIST_SMEM) {
 #pragma unroll
         for (int d = 0; d < D; d++)
-            for (uint32_t i = threadIdx.x; i < (p.def[d].num_states + 1) * 256u; i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
+            for (uint32_t i = threadIdx.x; i < (p.def[d].num_states + 1) * bcols; i += blockDim.x) sts32(base_s + lay.hist[d] + i * 4, 0u);
     } else {
 #pragma unroll
         for (int d = 0; d < D; d++)
@@ -285,8 +294,9 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
         }
     };
     const uint32_t cache_log2 = p.hist_cache_log2;
-    auto count = [&](int d, uint32_t cur, uint32_t c) {
-        if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> NSH) << 8) | c) * 4);
+    auto count = [&](int d, uint32_t cur, uint32_t c, uint32_t cent) {
+        if (CBINS) red_shared_inc(hist_s[d] + ((cur >> NSH) * bcols + (cent >> 24)) * 4);
+        else if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> NSH) << 8) | c) * 4);
         else {
             // bin cache: slot = {key, count}; a slot is claimed by the first key that hashes to it and never changes owner,
             // every other key of that slot goes to the global bins (exact either way)
@@ -474,7 +484,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                                 const uint32_t e = lookup(d, cur[d], c, cent);
                                 if (HM == (int)HIST_SMEM && SB == 1 && !E16)   // bin index (state << 8 | byte) in one byte permute
                                     red_shared_inc(hist_s[d] + prmt(cur[d], w[q], 0x3324u + j) * 4);
-                                else count(d, cur[d], c);
+                                else count(d, cur[d], c, cent);
                                 before[d][j] = cur[d];
                                 cur[d] = e;
                             }
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                             const uint32_t stv = (pos <= L) ? (cur[d] >> NSH) : p.def[d].num_states;   // state, final state, then dummy
                             if (pos < L) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);
-                                count(d, cur[d], c);
+                                count(d, cur[d], c, cent);
                                 acc |= e;
                                 cur[d] = e;
                             }
@@ -643,6 +653,14 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t S = p.def[d].num_states;
+            if (CBINS && bcols < 256u) {   // compact bins: column k stands for byte bin_byte[k]; the last column is nobody's
+                for (uint32_t i = threadIdx.x; i < S * bcols; i += blockDim.x) {
+                    const uint32_t s = i / bcols, k = i - s * bcols;
+                    const uint32_t v = lds32(hist_s[d] + i * 4);
+                    if (v && k + 1 < bcols) atomicAdd(p.def[d].hist + (size_t)__ldg(p.bin_byte + k) * S + s, (unsigned long long)v);
+                }
+                continue;
+            }
             for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) {
                 const uint32_t s = i >> 8, c = i & 255u;
                 const uint32_t v = lds32(hist_s[d] + i * 4);
