@@ -112,7 +112,7 @@ static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int 
     // (single copy: the 16-bit entries win at every size measured — two entries per bank word halve the conflicts and
     //  the footprint: 3-def set 28.9 % -> 31.9 % of HBM peak, 2-def 40.1 -> 43.3, 1023-state DFA 2.2x)
     const uint32_t P16 = TABLE_PLAIN16, P32 = TABLE_PLAIN;
-    // (TABLE_REPL16 is only taken when asked for: see DESIGN, "three defs")
+    // (TABLE_REPL16 is not in the fall-back order below: it is taken by the rule above, or when asked for)
     const uint32_t order[][2] = {{TABLE_REPL, HIST_SMEM}, {P16, HIST_SMEM}, {TABLE_REPL, HIST_GLOBAL}, {P16, HIST_GLOBAL},
                                  {P32, HIST_SMEM}, {P32, HIST_GLOBAL}, {TABLE_GLOBAL, HIST_GLOBAL}, {TABLE_REPL16, HIST_SMEM}, {TABLE_REPL16, HIST_GLOBAL}};
     // a handful of tiles (the reference's one-string call): one CTA walks them, and staging 100 KB of replicated tables for it costs
