@@ -121,7 +121,7 @@ extern "C" {
 
 int b2r_column_to_fr(b2r_config* c, const void* d_col, uint32_t kind, const uint64_t* d_offsets, uint64_t n_strings, uint64_t rows, uint64_t pitch,
                      uint64_t* d_fr, void* cuda_stream) {
-    if (!c || !d_fr || (!d_col && n_strings * rows && kind != B2R_COL_ENABLE)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
+    if (!c || !d_fr || (!d_col && n_strings != 0 && rows != 0 && kind != B2R_COL_ENABLE)) { set_error("null argument"); return B2R_ERR_INVALID_ARG; }
     if (c->device < 0) { set_error("this handle was created without a device (device = -1): no CPU fallback exists"); return B2R_ERR_CUDA; }
     if (kind < B2R_COL_U8 || kind > B2R_COL_ENABLE) { set_error("unknown column kind %u", kind); return B2R_ERR_INVALID_ARG; }
     if ((kind == B2R_COL_CHARS || kind == B2R_COL_ENABLE) && !d_offsets && n_strings) { set_error("offsets are required for this column kind"); return B2R_ERR_INVALID_ARG; }

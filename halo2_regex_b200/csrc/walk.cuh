@@ -175,10 +175,10 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     // ---- stage the tables ----------------------------------------------------------------------------------------------
     if (SMEM_TAB) {
         constexpr uint32_t csh = REPL ? 5u : 0u;   // log2(copies)
-#pragma unroll
         // (four global loads per thread in flight, then their stores: the shared-memory stores are compiler barriers, and a loop of
         //  load -> store round trips made the prologue of a one-string launch 100 us long)
         constexpr int SU = 4;
+#pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t n = p.def[d].num_classes * p.def[d].padded_states;
             const uint32_t t0 = base_s + lay.tab[d];
