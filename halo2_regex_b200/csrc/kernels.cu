@@ -88,7 +88,7 @@ static int plan_walk_tables(WalkParams& p, bool wide, int force_table_mode, int 
         if (tm != TABLE_GLOBAL) {
             const uint32_t stride = walk_stride(tm);
             for (uint32_t d = 0; d < p.n_defs; d++)
-                if ((uint64_t)p.def[d].padded_states * stride > 65536u) return false;   // the entry's low bits hold next*stride
+                if ((uint64_t)p.def[d].padded_states * stride > 65536u || (tm == TABLE_REPL16 && p.def[d].padded_states > 512u)) return false;   // the entry's low bits hold next*stride (pair-packed: (next >> 1) << 7 in 16 bits)
         }
         uint64_t bins = 0;
         for (uint32_t d = 0; d < p.n_defs; d++) bins += (uint64_t)(p.def[d].num_states + 1) * walk_bin_cols(p) * 4u;

@@ -97,8 +97,8 @@ constexpr uint32_t TABLE_REPL = 0;   // shared memory, one copy of every entry p
 constexpr uint32_t TABLE_PLAIN = 1;  // shared memory, one copy (stride 4 B)
 constexpr uint32_t TABLE_GLOBAL = 2; // global memory (L1/L2)
 constexpr uint32_t TABLE_PLAIN16 = 3; // shared memory, one copy of 16-bit entries (next << 1 | rare): half the size, for large DFAs
-constexpr uint32_t TABLE_REPL16 = 4;  // shared memory, 16-bit entries (next << 6 | rare) replicated once per lane (stride 64 B: two lanes share a bank word,
-                                      // no conflict): conflict-free lookups at half the footprint of TABLE_REPL — several small DFAs side by side
+constexpr uint32_t TABLE_REPL16 = 4;  // shared memory, 16-bit entries replicated once per lane, the entries of two adjacent states in one 32-bit word per lane
+                                      // (lane l always reads bank l): conflict-free lookups at half the footprint of TABLE_REPL — several small DFAs side by side
 // HIST_SMEM: dense bins [state][byte] in shared memory.  HIST_GLOBAL (bins too large for that): 64-bit atomics on the global
 // bins, behind a shared-memory cache of (key, count) slots that absorbs the hot (byte, state) pairs.
 constexpr uint32_t HIST_NONE = 0, HIST_SMEM = 1, HIST_GLOBAL = 2;

@@ -163,11 +163,18 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
     constexpr bool REPL = TM == (int)TABLE_REPL || TM == (int)TABLE_REPL16;   // one copy of every entry per lane
     constexpr bool E16 = TM == (int)TABLE_PLAIN16 || TM == (int)TABLE_REPL16;   // 16-bit entries: next << NSH | rare, next << NSH = next * stride
                                                                         // (else next << 16 | next * stride | rare)
-    constexpr uint32_t NSH = TM == (int)TABLE_REPL16 ? 6u : E16 ? 1u : 16u;   // entry >> NSH = the state
-    constexpr uint32_t EMASK = TM == (int)TABLE_REPL16 ? 0xFFC0u : 0xFFFEu;   // 16-bit entries: the bits of next * stride
+    // TABLE_REPL16 is PAIR-PACKED: the entries of the adjacent states 2m and 2m+1 (same class) share one 32-bit word per lane, i.e. one
+    // 128-byte block per state pair with lane l's word at + l*4 and state 2m+1 in its upper half.  Lane l then reads bank l whatever its
+    // state (a 64-byte stride per state puts two lanes in one bank word and costs a replay whenever the two need different entries).
+    // Entry = (next >> 1) << 7 | (next & 1) << 1 | rare: masked with EMASK it IS the byte offset of state `next` inside a class row.
+    constexpr bool PAIR = TM == (int)TABLE_REPL16;
+    constexpr uint32_t NSH = E16 ? 1u : 16u;                             // entry >> NSH = the state (not for PAIR: stof below)
+    constexpr uint32_t EMASK = PAIR ? 0xFF82u : 0xFFFEu;                 // 16-bit entries: the bits of the state's byte offset
+    auto stof = [](uint32_t e) -> uint32_t { return PAIR ? ((e >> 6) | ((e >> 1) & 1u)) : (e >> NSH); };   // entry -> state
+    auto enc16 = [](uint32_t st) -> uint32_t { return PAIR ? (((st >> 1) << 7) | ((st & 1u) << 1)) : (st << 1); };   // state -> 16-bit entry (rare = 0)
     constexpr uint32_t stride = TM == (int)TABLE_REPL ? 128u : TM == (int)TABLE_REPL16 ? 64u : TM == (int)TABLE_PLAIN ? 4u : E16 ? 2u : 0u;
     const uint32_t cstride = REPL ? 128u : (p.cls_repl ? 128u : 4u);      // class-table entry stride (a constant for replicated tables)
-    const uint32_t laneoff = TM == (int)TABLE_REPL ? (uint32_t)lane * 4u : TM == (int)TABLE_REPL16 ? (uint32_t)lane * 2u : 0u;
+    const uint32_t laneoff = REPL ? (uint32_t)lane * 4u : 0u;
     const uint32_t claneoff = (REPL || p.cls_repl) ? (uint32_t)lane * 4u : 0u;   // the class table holds 32-bit entries in either case
     constexpr bool CBINS = E16 && HM == (int)HIST_SMEM && D >= 2 && D <= 3;   // compact bins possible (walk_bin_cols decides)
     const uint32_t bcols = walk_bin_cols(p);
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                     // single-copy tables: row k is XOR-swizzled by its class (walk_swizzle) — lanes in the same state with
                     // different classes would otherwise all hit one bank (the row size is a power of two)
                     const uint32_t swz = REPL ? 0u : walk_swizzle(idx / p.def[d].padded_states, p.def[d].padded_states * stride);
-                    if (TM == (int)TABLE_REPL16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + idx * 64 + l * 2), "h"((unsigned short)(((e >> 16) << 6) | (e & 1u))) : "memory");
+                    if (PAIR) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + (idx >> 1) * 128 + l * 4 + (idx & 1u) * 2), "h"((unsigned short)(enc16(e >> 16) | (e & 1u))) : "memory");
                     else if (E16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(t0 + ((idx * 2) ^ swz)), "h"((unsigned short)(((e >> 16) << 1) | (e & 1u))) : "memory");
                     else sts32(t0 + ((idx * stride) ^ swz) + l * 4, e | ((e >> 16) * stride));
                 }
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                 uint32_t v;
                 if (D == 1) {
                     const uint32_t k = kv4[u][0], rb = p.def[0].padded_states * stride;
-                    v = base_s + lay.tab[0] + k * rb + (TM == (int)TABLE_REPL16 ? l * 2 : TM == (int)TABLE_REPL ? l * 4 : 0u) + (REPL ? 0u : walk_swizzle(k, rb));
+                    v = base_s + lay.tab[0] + k * rb + (REPL ? l * 4 : 0u) + (REPL ? 0u : walk_swizzle(k, rb));
                 } else {
                     v = 0;
 #pragma unroll
@@ -290,17 +297,17 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
             return lds32((cur & 0xFFFCu) ^ row);
         } else {
             const uint32_t k = __ldg(p.def[d].byte_class + c);
-            return __ldg(p.def[d].hot + k * p.def[d].padded_states + (cur >> NSH));
+            return __ldg(p.def[d].hot + k * p.def[d].padded_states + stof(cur));
         }
     };
     const uint32_t cache_log2 = p.hist_cache_log2;
     auto count = [&](int d, uint32_t cur, uint32_t c, uint32_t cent) {
-        if (CBINS) red_shared_inc(hist_s[d] + ((cur >> NSH) * bcols + (cent >> 24)) * 4);
-        else if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + (((cur >> NSH) << 8) | c) * 4);
+        if (CBINS) red_shared_inc(hist_s[d] + (stof(cur) * bcols + (cent >> 24)) * 4);
+        else if (HM == (int)HIST_SMEM) red_shared_inc(hist_s[d] + ((stof(cur) << 8) | c) * 4);
         else {
             // bin cache: slot = {key, count}; a slot is claimed by the first key that hashes to it and never changes owner,
             // every other key of that slot goes to the global bins (exact either way)
-            const uint32_t s = cur >> NSH;
+            const uint32_t s = stof(cur);
             if (s < p.def[d].num_states) {
                 const uint32_t key = ((s << 8) | c) + 1u;
                 // keys and counts in two arrays (not {key, count} pairs: those would put every key in an even bank)
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < D; d++) {
             const uint32_t f = (p.def[d].init_states && valid) ? (uint32_t)p.def[d].init_states[idx] : p.def[d].first_state;
-            cur[d] = E16 ? (f << NSH) : (f << 16) | (f * stride);
+            cur[d] = E16 ? enc16(f) : (f << 16) | (f * stride);
         }
 
         // staging geometry
@@ -493,11 +500,11 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         for (int d = 0; d < D; d++) {
                             acc |= before[d][1] | before[d][2];           // entries of rows 4q, 4q+1 (3-input LOP3s)
                             acc |= before[d][3] | cur[d];                 // rows 4q+2, 4q+3
-                            if (E16) {                                    // 16-bit entries: the state is entry >> NSH
-                                if (SB == 1) pk[d][q] = (before[d][0] >> NSH) | ((before[d][1] >> NSH) << 8) | ((before[d][2] >> NSH) << 16) | ((before[d][3] >> NSH) << 24);
+                            if (E16) {                                    // 16-bit entries: the state is stof(entry)
+                                if (SB == 1) pk[d][q] = stof(before[d][0]) | (stof(before[d][1]) << 8) | (stof(before[d][2]) << 16) | (stof(before[d][3]) << 24);
                                 else {
-                                    pk[d][q * 2] = (before[d][0] >> NSH) | ((before[d][1] >> NSH) << 16);
-                                    pk[d][q * 2 + 1] = (before[d][2] >> NSH) | ((before[d][3] >> NSH) << 16);
+                                    pk[d][q * 2] = stof(before[d][0]) | (stof(before[d][1]) << 16);
+                                    pk[d][q * 2 + 1] = stof(before[d][2]) | (stof(before[d][3]) << 16);
                                 }
                             } else if (SB == 1) {                         // state bytes (entry byte 2) of four rows into one word
                                 const uint32_t lo = prmt(before[d][0], before[d][1], 0x4462u), hi = prmt(before[d][2], before[d][3], 0x4462u);
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
                         if (SMEM_TAB && pos < L) cent = lds32(cls_lane_s + c * cstride);
 #pragma unroll
                         for (int d = 0; d < D; d++) {
-                            const uint32_t stv = (pos <= L) ? (cur[d] >> NSH) : p.def[d].num_states;   // state, final state, then dummy
+                            const uint32_t stv = (pos <= L) ? stof(cur[d]) : p.def[d].num_states;   // state, final state, then dummy
                             if (pos < L) {
                                 const uint32_t e = lookup(d, cur[d], c, cent);
                                 count(d, cur[d], c, cent);
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(WALK_MAX_THREADS, 1) walk_kernel(const __grid_
 #endif
             uint32_t fin[D];
 #pragma unroll
-            for (int d = 0; d < D; d++) fin[d] = cur[d] >> NSH;
+            for (int d = 0; d < D; d++) fin[d] = stof(cur[d]);
             emitter.run_tile(tile_base, valid, valid && !too_long, off, L, fw0, fw1, fin, tot, /*filled=*/true, stash_g, stash_s);
 #ifdef B2R_PROBE
             const unsigned long long pr_t4 = gtime();
