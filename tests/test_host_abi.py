@@ -204,3 +204,20 @@ def test_workload_generators_agree():
     assert res.code == 0
     acc = (out.status["flags"] & 1).astype(bool)
     assert acc[plan["has_match"]].all()
+
+
+def test_every_documented_option_is_accepted():
+    """The knobs listed under b2r_config_set_option in include/b2r.h exist (a handle without a device takes options too);
+    an unknown name is an error, not a silent no-op."""
+    header = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    block = header[header.index("testing / tuning knobs of a handle"):header.index("int b2r_config_set_option")]
+    names = ["table_mode", "hist_mode", "fuse", "stagger_ns", "slices", "host_threads", "small_path", "sparse_cap", "sparse_direct", "trace_host",
+             "hist_cache_log2", "spread_fill", "long_fused", "debug", "host_debug"]
+    for name in names:
+        assert name in block, f"{name} is not documented in include/b2r.h"
+    cfg = product_config("regex1", 64, device=-1)
+    values = {"table_mode": "repl16", "hist_mode": "smem", "trace_host": "0", "debug": "0", "host_debug": "0"}
+    for name in names:
+        cfg.set_option(name, values.get(name, "1"))
+    with pytest.raises(Exception):
+        cfg.set_option("no_such_option", "1")
